@@ -1,0 +1,82 @@
+"""In-tree build of libzkfhe_b200.so with nvcc for sm_100a (no torch, no cmake).
+
+    python zk-fhe_b200/build.py [--force] [--verbose]
+
+The shared library lands in zk-fhe_b200/lib/ (git-ignored, but it travels to the
+GPU box with the gpurun snapshot).  `ff_ptx_gen.cuh` is regenerated from
+gen_ff_ptx.py first, which re-runs the instruction-level self check.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libzkfhe_b200.so")
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-Wall", "-diag-suppress", "177",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h", ".py")):
+                with open(os.path.join(root, name), "rb") as f:
+                    h.update(name.encode() + f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp_path = os.path.join(LIBDIR, ".stamp")
+    stamp = _stamp()
+    if (not force and os.path.exists(LIB) and os.path.exists(stamp_path)
+            and open(stamp_path).read() == stamp):
+        return LIB
+    subprocess.run([sys.executable, os.path.join(CSRC, "gen_ff_ptx.py")], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    stamp = _stamp()
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            print(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.run(cmd, check=True)
+    with open(stamp_path, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

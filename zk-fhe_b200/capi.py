@@ -1,0 +1,164 @@
+"""ctypes binding of libzkfhe_b200.so (the C ABI in include/zkfhe_b200.h).
+
+This is the Python face of the drop-in boundary: plain pointers and sizes, no
+torch types.  There is no CPU fallback -- if the library is missing it is
+built with nvcc (zk-fhe_b200/build.py); if that fails, or no CUDA device is
+present when a context is created, an exception is raised.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+HEADER = os.path.join(ROOT, "include", "zkfhe_b200.h")
+LIB_PATH = os.path.join(HERE, "lib", "libzkfhe_b200.so")
+
+OK = 0
+ERR_CUDA, ERR_ARG, ERR_STATE, ERR_ASSERT, ERR_OVERFLOW, ERR_UNSATISFIED = -1, -2, -3, -4, -5, -6
+ERROR_NAMES = {ERR_CUDA: "ZKFHE_ERR_CUDA", ERR_ARG: "ZKFHE_ERR_ARG", ERR_STATE: "ZKFHE_ERR_STATE",
+               ERR_ASSERT: "ZKFHE_ERR_ASSERT", ERR_OVERFLOW: "ZKFHE_ERR_OVERFLOW",
+               ERR_UNSATISFIED: "ZKFHE_ERR_UNSATISFIED"}
+
+
+class ZkfheError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+def declared_symbols():
+    """Every function name declared in include/zkfhe_b200.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkfhe_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+_c = ctypes
+_u8p = _c.c_void_p          # raw addresses (host or device) are passed as integers
+_SIGNATURES = {
+    "zkfhe_init": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_destroy": (None, [_c.c_void_p]),
+    "zkfhe_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "zkfhe_version": (_c.c_char_p, []),
+    "zkfhe_set_stream": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "zkfhe_sync": (_c.c_int, [_c.c_void_p]),
+    "zkfhe_launch_count": (_c.c_uint64, [_c.c_void_p]),
+    "zkfhe_selftest": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_uint32)]),
+    "zkfhe_ntt_fr": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
+    "zkfhe_ntt_fr_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
+    "zkfhe_coeff_to_extended_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _u8p, _c.c_uint32, _c.c_uint32]),
+    "zkfhe_load_srs": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p, _u8p]),
+    "zkfhe_msm_g1": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
+    "zkfhe_msm_g1_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
+    "zkfhe_last_kernel_ms": (_c.c_float, [_c.c_void_p]),
+}
+
+
+def load_library(build_if_missing=True):
+    """dlopen the in-tree library (building it first if needed) and type its symbols."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise FileNotFoundError(f"{LIB_PATH} not built; run python zk-fhe_b200/build.py")
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_zkfhe_build", os.path.join(HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _addr(buf):
+    """Address of a host buffer (bytes-like / numpy) or pass through an int device pointer."""
+    if isinstance(buf, int):
+        return buf
+    if buf is None:
+        return None
+    if hasattr(buf, "ctypes"):                      # numpy
+        return buf.ctypes.data
+    if isinstance(buf, (bytearray, memoryview)):
+        return ctypes.addressof((ctypes.c_char * len(buf)).from_buffer(buf))
+    if isinstance(buf, bytes):
+        return ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value
+    raise TypeError(type(buf))
+
+
+class Context:
+    """One GPU, one stream.  Mirrors the zkfhe_ctx lifetime."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.zkfhe_init(device, ctypes.byref(h))
+        if rc != OK:
+            raise ZkfheError(rc, f"zkfhe_init(device={device}) failed: no usable CUDA device (no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zkfhe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise ZkfheError(rc, self.lib.zkfhe_last_error(self.h).decode())
+
+    # -- plumbing -----------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.zkfhe_set_stream(self.h, cuda_stream))
+
+    def sync(self):
+        self._check(self.lib.zkfhe_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.zkfhe_launch_count(self.h))
+
+    def last_kernel_ms(self):
+        return float(self.lib.zkfhe_last_kernel_ms(self.h))
+
+    def selftest(self, n_cases=1 << 16, seed=1):
+        bad = ctypes.c_uint32(0)
+        self._check(self.lib.zkfhe_selftest(self.h, n_cases, seed, ctypes.byref(bad)))
+        return bad.value
+
+    # -- stage (3) ----------------------------------------------------------
+    def ntt_fr(self, data, log_n, batch, inverse=False, coset=False):
+        """In place on a host buffer (bytearray / numpy uint8) of batch*2^log_n*32 bytes."""
+        self._check(self.lib.zkfhe_ntt_fr(self.h, _addr(data), log_n, batch, int(inverse), int(coset)))
+
+    def ntt_fr_dev(self, d_ptr, log_n, batch, inverse=False, coset=False):
+        self._check(self.lib.zkfhe_ntt_fr_dev(self.h, d_ptr, log_n, batch, int(inverse), int(coset)))
+
+    def coeff_to_extended_dev(self, d_coeffs, log_n_in, d_ext, log_n_out, batch):
+        self._check(self.lib.zkfhe_coeff_to_extended_dev(self.h, d_coeffs, log_n_in, d_ext, log_n_out, batch))
+
+    # -- stage (2) ----------------------------------------------------------
+    def load_srs(self, k, g=None, g_lagrange=None):
+        self._check(self.lib.zkfhe_load_srs(self.h, k, _addr(g), _addr(g_lagrange)))
+        self.srs_k = k
+
+    def msm_g1(self, scalars, batch, basis=1):
+        out = bytearray(64 * batch)
+        self._check(self.lib.zkfhe_msm_g1(self.h, _addr(scalars), batch, basis, _addr(out)))
+        return bytes(out)
+
+    def msm_g1_dev(self, d_scalars, batch, basis, d_out):
+        self._check(self.lib.zkfhe_msm_g1_dev(self.h, d_scalars, batch, basis, d_out))

@@ -1,0 +1,253 @@
+// C ABI of libzkfhe_b200 (include/zkfhe_b200.h): context lifecycle, host<->device
+// staging and the on-device self test.  Compute lives in ntt.cu / msm.cu /
+// witness.cu; nothing here falls back to the CPU.
+#include <new>
+#include "common.cuh"
+
+using namespace zkfhe;
+
+namespace zkfhe {
+
+// ---- self test ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <int F> __device__ fe<F> random_fe(uint64_t& s) {
+    fe<F> a;
+    for (int i = 0; i < 8; i += 2) {
+        uint64_t z = splitmix(s);
+        a.v[i] = (uint32_t)z;
+        a.v[i + 1] = (uint32_t)(z >> 32);
+    }
+    a.v[7] &= 0x1fffffffu;   // < 2^253 < modulus
+    return a;
+}
+
+template <int F> __device__ uint32_t selftest_field(uint64_t& s) {
+    uint32_t bad = 0;
+    fe<F> a = random_fe<F>(s), b = random_fe<F>(s), c = random_fe<F>(s);
+    if (!eq(mul(a, b), mul_c(a, b))) bad++;
+    if (!eq(sqr(a), mul_c(a, a))) bad++;
+    if (!eq(sub(add(a, b), b), a)) bad++;
+    if (!eq(add(sub(a, b), b), a)) bad++;
+    if (!eq(mul(a, add(b, c)), add(mul(a, b), mul(a, c)))) bad++;
+    if (!eq(from_mont(to_mont(a)), a)) bad++;
+    if (!eq(add(a, neg(a)), fe_zero<F>())) bad++;
+    // edge operands
+    fe<F> m1 = sub(fe_zero<F>(), fe_one<F>());
+    if (!eq(mul(m1, m1), fe_one<F>())) bad++;
+    if (!eq(mul(a, fe_one<F>()), a)) bad++;
+    if (!is_zero(mul(a, fe_zero<F>()))) bad++;
+    return bad;
+}
+
+__global__ void k_selftest(uint32_t n_cases, uint64_t seed, uint32_t* mismatches) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cases) return;
+    uint64_t s = seed + 0x1234567ull * i;
+    uint32_t bad = selftest_field<FR>(s) + selftest_field<FQ>(s);
+    if (i < 64) {   // inversions and curve identities on a few threads only
+        fr_t a = random_fe<FR>(s);
+        if (!is_zero(a) && !eq(mul(a, inv(a)), fe_one<FR>())) bad++;
+        fq_t q = random_fe<FQ>(s);
+        if (!is_zero(q) && !eq(mul(q, inv(q)), fe_one<FQ>())) bad++;
+        // G = (1, 2) in Montgomery form; check 2G + G == 3G via two routes and the curve equation
+        g1_affine g;
+        g.x = fe_one<FQ>();
+        g.y = add(fe_one<FQ>(), fe_one<FQ>());
+        g1_xyzz d = xyzz_dbl_affine(g);
+        g1_xyzz t1 = d;
+        xyzz_madd(t1, g, false);                       // 2G + G
+        g1_xyzz t2 = xyzz_from_affine(g);
+        xyzz_add(t2, d);                               // G + 2G
+        g1_affine a1 = xyzz_to_affine(t1), a2 = xyzz_to_affine(t2);
+        if (!eq(a1.x, a2.x) || !eq(a1.y, a2.y)) bad++;
+        fq_t three = add(add(fe_one<FQ>(), fe_one<FQ>()), fe_one<FQ>());
+        if (!eq(sqr(a1.y), add(mul(sqr(a1.x), a1.x), three))) bad++;
+        g1_xyzz z = t1;
+        xyzz_madd(z, a1, true);                        // 3G - 3G = identity
+        if (!is_identity(z)) bad++;
+        g1_xyzz dd = t1;
+        xyzz_madd(dd, a1, false);                      // 3G + 3G via the doubling branch
+        g1_xyzz d2 = xyzz_dbl(t2);
+        g1_affine b1 = xyzz_to_affine(dd), b2 = xyzz_to_affine(d2);
+        if (!eq(b1.x, b2.x) || !eq(b1.y, b2.y)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches) {
+    uint32_t* d_bad;
+    ZK_CUDA(ctx, cudaMalloc(&d_bad, 4));
+    ZK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    k_selftest<<<(n_cases + 127) / 128, 128, 0, ctx->stream>>>(n_cases, seed, d_bad);
+    ZK_CHECK_LAUNCH(ctx);
+    ZK_CUDA(ctx, cudaMemcpyAsync(mismatches, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaFree(d_bad));
+    return ZKFHE_OK;
+}
+
+}  // namespace zkfhe
+
+// ---- lifecycle ---------------------------------------------------------------------------
+extern "C" {
+
+const char* zkfhe_version(void) { return "zkfhe_b200 0.1 (sm_100a)"; }
+
+int zkfhe_init(int device, zkfhe_ctx** out) {
+    if (!out) return ZKFHE_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return ZKFHE_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ZKFHE_ERR_CUDA;
+    zkfhe_ctx* ctx = new (std::nothrow) zkfhe_ctx();
+    if (!ctx) return ZKFHE_ERR_CUDA;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ZKFHE_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return ZKFHE_OK;
+}
+
+void zkfhe_destroy(zkfhe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->domains) { cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); }
+    for (auto& b : ctx->basis) if (b.table) cudaFree(b.table);
+    for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* zkfhe_last_error(const zkfhe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int zkfhe_set_stream(zkfhe_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ZKFHE_ERR_ARG;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cuda_stream == nullptr && !ctx->own_stream) {
+        ZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    } else if (cuda_stream != nullptr) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    }
+    return ZKFHE_OK;
+}
+
+int zkfhe_sync(zkfhe_ctx* ctx) {
+    if (!ctx) return ZKFHE_ERR_ARG;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+uint64_t zkfhe_launch_count(const zkfhe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx) {
+    if (!ctx) return -1.f;
+    float total = 0.f;
+    for (size_t i = 0; i < ctx->ev_used; i++) {
+        if (cudaEventSynchronize(ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pairs[i].first, ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
+        total += ms;
+    }
+    return total;
+}
+
+int zkfhe_selftest(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches) {
+    if (!ctx || !mismatches) return ZKFHE_ERR_ARG;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return selftest_run(ctx, n_cases, seed, mismatches);
+}
+
+// ---- NTT ---------------------------------------------------------------------------------
+int zkfhe_ntt_fr_dev(zkfhe_ctx* ctx, uint8_t* d_data, uint32_t log_n, uint32_t batch, int inverse, int coset) {
+    if (!ctx || !d_data) return fail(ctx, ZKFHE_ERR_ARG, "ntt: null pointer");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    fr_t* d = reinterpret_cast<fr_t*>(d_data);
+    uint64_t n = 1ull << log_n;
+    return ntt_run(ctx, d, n, (uint32_t)n, d, n, log_n, batch, inverse, coset);
+}
+
+int zkfhe_ntt_fr(zkfhe_ctx* ctx, uint8_t* h_data, uint32_t log_n, uint32_t batch, int inverse, int coset) {
+    if (!ctx || !h_data) return fail(ctx, ZKFHE_ERR_ARG, "ntt: null pointer");
+    if (log_n < 1 || log_n > 22) return fail(ctx, ZKFHE_ERR_ARG, "ntt: log_n=%u out of range [1,22]", log_n);
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = ((size_t)batch << log_n) * sizeof(fr_t);
+    if (bytes == 0) return ZKFHE_OK;
+    void* d;
+    ZK_TRY(ws_get(ctx, "ntt_io", bytes, &d));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d, h_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(zkfhe_ntt_fr_dev(ctx, (uint8_t*)d, log_n, batch, inverse, coset));
+    ZK_CUDA(ctx, cudaMemcpyAsync(h_data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_coeff_to_extended_dev(zkfhe_ctx* ctx, const uint8_t* d_coeffs, uint32_t log_n_in, uint8_t* d_ext,
+                                uint32_t log_n_out, uint32_t batch) {
+    if (!ctx || !d_coeffs || !d_ext) return fail(ctx, ZKFHE_ERR_ARG, "coeff_to_extended: null pointer");
+    if (log_n_in > log_n_out) return fail(ctx, ZKFHE_ERR_ARG, "coeff_to_extended: log_n_in > log_n_out");
+    if (log_n_out < 12 && (const void*)d_coeffs == (const void*)d_ext && log_n_in != log_n_out)
+        return fail(ctx, ZKFHE_ERR_ARG, "coeff_to_extended: in-place needs equal sizes");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, reinterpret_cast<const fr_t*>(d_coeffs), 1ull << log_n_in, 1u << log_n_in,
+                   reinterpret_cast<fr_t*>(d_ext), 1ull << log_n_out, log_n_out, batch, 0, 1);
+}
+
+// ---- MSM ---------------------------------------------------------------------------------
+int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t* h_g_lagrange) {
+    if (!ctx) return ZKFHE_ERR_ARG;
+    if (k < 1 || k > 22) return fail(ctx, ZKFHE_ERR_ARG, "load_srs: k=%u out of range [1,22]", k);
+    if (!h_g && !h_g_lagrange) return fail(ctx, ZKFHE_ERR_ARG, "load_srs: both bases are null");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = ((size_t)1 << k) * sizeof(g1_affine);
+    void* d;
+    ZK_TRY(ws_get(ctx, "srs_stage", bytes, &d));
+    const uint8_t* src[2] = {h_g, h_g_lagrange};
+    for (int which = 0; which < 2; which++) {
+        if (!src[which]) continue;
+        ZK_CUDA(ctx, cudaMemcpyAsync(d, src[which], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_TRY(msm_load_basis(ctx, which, (const g1_affine*)d, k));
+    }
+    ctx->srs_k = k;
+    return ZKFHE_OK;
+}
+
+int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, uint8_t* d_out_affine) {
+    if (!ctx || !d_scalars || !d_out_affine) return fail(ctx, ZKFHE_ERR_ARG, "msm: null pointer");
+    if (ctx->srs_k == 0) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return msm_run(ctx, reinterpret_cast<const fr_t*>(d_scalars), 1ull << ctx->srs_k, ctx->srs_k, batch, basis,
+                   reinterpret_cast<g1_affine*>(d_out_affine));
+}
+
+int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int basis, uint8_t* h_out_affine) {
+    if (!ctx || !h_scalars || !h_out_affine) return fail(ctx, ZKFHE_ERR_ARG, "msm: null pointer");
+    if (ctx->srs_k == 0) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
+    if (batch == 0) return ZKFHE_OK;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t sbytes = ((size_t)batch << ctx->srs_k) * sizeof(fr_t), obytes = (size_t)batch * sizeof(g1_affine);
+    void *d_s, *d_o;
+    ZK_TRY(ws_get(ctx, "msm_in", sbytes, &d_s));
+    ZK_TRY(ws_get(ctx, "msm_out", obytes, &d_o));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_s, h_scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(zkfhe_msm_g1_dev(ctx, (const uint8_t*)d_s, batch, basis, (uint8_t*)d_o));
+    ZK_CUDA(ctx, cudaMemcpyAsync(h_out_affine, d_o, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Shared host-side plumbing for libzkfhe_b200: the context object behind the C
+// ABI (include/zkfhe_b200.h), error reporting and device workspace management.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ec.cuh"
+#include "../../include/zkfhe_b200.h"
+
+namespace zkfhe {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+// Pippenger layout for one SRS basis (resident across proofs).
+struct MsmBasis {
+    g1_affine* table = nullptr;   // [W][n] : table[w*n + i] = 2^(c*w) * P_i  (affine, Montgomery)
+    uint32_t log_n = 0, c = 0, W = 0;
+    bool loaded = false;
+};
+
+struct NttDomain {
+    fr_t* tw_fwd = nullptr;   // omega^i,  i < n
+    fr_t* tw_inv = nullptr;   // omega^-i, i < n
+    fr_t n_inv;               // host copy (Montgomery), passed by value to kernels
+};
+
+}  // namespace zkfhe
+
+struct zkfhe_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;                       // kernels launched through this ctx
+    std::map<uint32_t, zkfhe::NttDomain> domains;   // by log_n
+    zkfhe::MsmBasis basis[2];                    // 0: coefficient basis g, 1: Lagrange basis
+    uint32_t srs_k = 0;
+    std::map<std::string, zkfhe::DevBuf> ws;     // named, grow-only workspaces
+    // CUDA-event pairs bracketing the dominant kernel(s) of the last NTT / MSM call
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
+    size_t ev_used = 0;
+};
+
+namespace zkfhe {
+
+inline int fail(zkfhe_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define ZK_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return zkfhe::fail(ctx, ZKFHE_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,      \
+                               cudaGetErrorString(e__));                                            \
+    } while (0)
+
+#define ZK_CHECK_LAUNCH(ctx)                                                                        \
+    do {                                                                                            \
+        (ctx)->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess)                                                                     \
+            return zkfhe::fail(ctx, ZKFHE_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,         \
+                               cudaGetErrorString(e__));                                            \
+    } while (0)
+
+#define ZK_TRY(expr)                  \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != ZKFHE_OK) return rc__; \
+    } while (0)
+
+inline int timed_begin(zkfhe_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pairs.size()) {
+        cudaEvent_t a, b;
+        ZK_CUDA(ctx, cudaEventCreate(&a));
+        ZK_CUDA(ctx, cudaEventCreate(&b));
+        ctx->ev_pairs.emplace_back(a, b);
+    }
+    ZK_CUDA(ctx, cudaEventRecord(ctx->ev_pairs[ctx->ev_used].first, ctx->stream));
+    return ZKFHE_OK;
+}
+inline int timed_end(zkfhe_ctx* ctx) {
+    ZK_CUDA(ctx, cudaEventRecord(ctx->ev_pairs[ctx->ev_used].second, ctx->stream));
+    ctx->ev_used++;
+    return ZKFHE_OK;
+}
+
+// Grow-only named workspace.  Reallocation synchronises the stream first.
+inline int ws_get(zkfhe_ctx* ctx, const char* name, size_t bytes, void** out) {
+    DevBuf& b = ctx->ws[name];
+    if (b.bytes < bytes) {
+        if (b.p) {
+            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ZK_CUDA(ctx, cudaFree(b.p));
+            b.p = nullptr;
+            b.bytes = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        ZK_CUDA(ctx, cudaMalloc(&b.p, want));
+        b.bytes = want;
+    }
+    *out = b.p;
+    return ZKFHE_OK;
+}
+
+// ---- entry points implemented in the .cu files (device-pointer level) ----------
+int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out);
+int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_len, fr_t* d_out,
+            uint64_t out_stride, uint32_t log_n, uint32_t batch, int inverse, int coset);
+int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n);
+int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log_n, uint32_t batch,
+            int which, g1_affine* d_out);
+int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches);
+
+}  // namespace zkfhe

@@ -1,0 +1,293 @@
+// Batched Pippenger MSM over BN254 G1 for sm_100a (stage (2) of the prove path).
+//
+// Replaces halo2-axiom `ParamsKZG::{commit, commit_lagrange}` ->
+// `arithmetic::best_multiexp` [UPSTREAM, un-vendored; SURVEY.md §8 a19]: for each
+// of `batch` columns, out = sum_i s_i * P_i over the n = 2^k points of one SRS
+// basis.  The affine result is mathematically unique, so parity with the CPU
+// prover is equality with oracle/curve.py `msm_naive`.
+//
+// Design (B200-first, not the CPU algorithm):
+//  * The SRS is fixed for the life of the prover and HBM is large, so every base
+//    point is expanded once into W = ceil(255/c) fixed-base multiples
+//    2^(c*w) * P_i (affine).  All W windows of a scalar then fall into ONE set of
+//    2^(c-1) signed-digit buckets per column: one bucket reduction per column
+//    instead of W.
+//  * Per column: (1) one CTA recodes the scalars into signed c-bit digits and
+//    counting-sorts the (point, sign) references by bucket in shared memory;
+//    (2) buckets are cut into segments of <= SEG references and one thread sums
+//    each segment with mixed XYZZ additions -- witness columns are full of
+//    repeated small values, so bucket sizes are heavily skewed and per-bucket
+//    threads would serialise; (3) one CTA per column folds the segment sums with
+//    the running-sum trick, each thread owning a contiguous bucket range, then a
+//    shared-memory tree reduction and a single inversion give the affine point.
+//  * The hot loop (2) gathers 64-byte affine points from the L2-resident table;
+//    scalars are read once, coalesced.
+#include "common.cuh"
+
+namespace zkfhe {
+
+static constexpr uint32_t SEG = 64;          // max point references summed by one thread
+static constexpr uint32_t RED_THREADS = 256; // threads of the per-column reduction CTA
+
+// ---- fixed-base table ---------------------------------------------------------------------
+__global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint32_t n, uint32_t c, uint32_t W) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine p = affine_load(bases + i);
+    affine_store(table + i, p);
+    g1_xyzz q = xyzz_from_affine(p);
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t d = 0; d < c; d++) q = xyzz_dbl(q);
+        g1_affine a = xyzz_to_affine(q);
+        affine_store(table + (size_t)w * n + i, a);
+        q = xyzz_from_affine(a);     // keep Z = 1 so the next doublings stay cheap
+    }
+}
+
+// ---- digit recoding -----------------------------------------------------------------------
+// bits [off, off+c) of a 256-bit little-endian integer, c <= 16
+__device__ __forceinline__ uint32_t get_bits(const fr_t& s, uint32_t off, uint32_t c) {
+    uint32_t limb = off >> 5, sh = off & 31;
+    uint64_t two = s.v[limb];
+    if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+    return (uint32_t)(two >> sh) & ((1u << c) - 1);
+}
+
+// Calls f(w, bucket_index, negative) for every non-zero signed digit of the scalar.
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const fr_t& s_canon, uint32_t c, uint32_t W, Fn f) {
+    uint32_t carry = 0;
+    const uint32_t halfw = 1u << (c - 1);
+    for (uint32_t w = 0; w < W; w++) {
+        uint32_t off = w * c;
+        uint32_t d = (off < 256 ? get_bits(s_canon, off, (off + c <= 256) ? c : 256 - off) : 0) + carry;
+        if (d > halfw) {
+            carry = 1;
+            uint32_t mag = (1u << c) - d;           // digit = d - 2^c < 0
+            if (mag) f(w, mag - 1, true);
+        } else {
+            carry = 0;
+            if (d) f(w, d - 1, false);
+        }
+    }
+}
+
+// One CTA per column: histogram -> exclusive scans -> scatter (counting sort by bucket).
+//   bucket_off[col][NB+1] : start of each bucket in sorted[col]
+//   seg_off[col][NB+1]    : first segment id of each bucket (segments of <= SEG references)
+//   sorted[col][..]       : (w*n + i) | sign<<31, grouped by bucket
+extern __shared__ uint32_t msm_smem[];
+
+__global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
+                                                   uint32_t W, uint32_t* bucket_off, uint32_t* seg_off,
+                                                   uint32_t* sorted, uint64_t sorted_stride) {
+    const uint32_t NB = 1u << (c - 1);
+    uint32_t* cnt = msm_smem;                 // [NB] counts, then running cursors
+    __shared__ uint32_t warp_tot[2][32];
+    const uint32_t col = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const fr_t* sc = scalars + (uint64_t)col * stride;
+    uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    uint32_t* soff = seg_off + (size_t)col * (NB + 1);
+    uint32_t* out = sorted + (uint64_t)col * sorted_stride;
+
+    for (uint32_t b = tid; b < NB; b += nt) cnt[b] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += nt) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s, c, W, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
+    }
+    __syncthreads();
+
+    // exclusive scan of counts (entries) and of ceil(count/SEG) (segments); NB = per * nt chunks
+    const uint32_t per = (NB + nt - 1) / nt;
+    const uint32_t b0 = tid * per;
+    uint32_t sum_e = 0, sum_s = 0;
+    for (uint32_t k = 0; k < per; k++) {
+        uint32_t b = b0 + k;
+        if (b < NB) { uint32_t v = cnt[b]; sum_e += v; sum_s += (v + SEG - 1) / SEG; }
+    }
+    // block-wide exclusive scan of (sum_e, sum_s)
+    uint32_t lane = tid & 31, wid = tid >> 5;
+    uint32_t inc_e = sum_e, inc_s = sum_s;
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t te = __shfl_up_sync(0xffffffffu, inc_e, d);
+        uint32_t ts = __shfl_up_sync(0xffffffffu, inc_s, d);
+        if (lane >= d) { inc_e += te; inc_s += ts; }
+    }
+    if (lane == 31) { warp_tot[0][wid] = inc_e; warp_tot[1][wid] = inc_s; }
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t nw = (nt + 31) / 32;
+        uint32_t ve = lane < nw ? warp_tot[0][lane] : 0, vs = lane < nw ? warp_tot[1][lane] : 0;
+        uint32_t ie = ve, is = vs;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            uint32_t te = __shfl_up_sync(0xffffffffu, ie, d);
+            uint32_t ts = __shfl_up_sync(0xffffffffu, is, d);
+            if (lane >= d) { ie += te; is += ts; }
+        }
+        warp_tot[0][lane] = ie - ve;   // exclusive warp offsets
+        warp_tot[1][lane] = is - vs;
+    }
+    __syncthreads();
+    uint32_t run_e = warp_tot[0][wid] + inc_e - sum_e;
+    uint32_t run_s = warp_tot[1][wid] + inc_s - sum_s;
+    for (uint32_t k = 0; k < per; k++) {
+        uint32_t b = b0 + k;
+        if (b < NB) {
+            uint32_t v = cnt[b];
+            boff[b] = run_e;
+            soff[b] = run_s;
+            cnt[b] = run_e;            // becomes the scatter cursor
+            run_e += v;
+            run_s += (v + SEG - 1) / SEG;
+        }
+    }
+    if (tid == nt - 1) { boff[NB] = run_e; soff[NB] = run_s; }
+    __syncthreads();
+
+    for (uint32_t i = tid; i < n; i += nt) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
+            uint32_t pos = atomicAdd(&cnt[b], 1u);
+            out[pos] = (w * n + i) | (negative ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// One thread per segment: sum <= SEG signed table points (mixed XYZZ adds).
+__global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restrict__ table, uint32_t c,
+                                                        const uint32_t* __restrict__ bucket_off,
+                                                        const uint32_t* __restrict__ seg_off,
+                                                        const uint32_t* __restrict__ sorted, uint64_t sorted_stride,
+                                                        g1_xyzz* partial, uint64_t partial_stride) {
+    const uint32_t NB = 1u << (c - 1);
+    const uint32_t col = blockIdx.y;
+    const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    const uint32_t* soff = seg_off + (size_t)col * (NB + 1);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= soff[NB]) return;
+    // bucket b with soff[b] <= s < soff[b+1]  (empty buckets have soff[b] == soff[b+1])
+    uint32_t lo = 0, hi = NB;               // invariant: soff[lo] <= s < soff[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (soff[mid] <= s) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t start = boff[b] + (s - soff[b]) * SEG;
+    const uint32_t end = min(start + SEG, boff[b + 1]);
+    const uint32_t* ref = sorted + (uint64_t)col * sorted_stride;
+    g1_xyzz acc = xyzz_identity();
+    for (uint32_t k = start; k < end; k++) {
+        uint32_t e = ref[k];
+        g1_affine pt = affine_load(table + (e & 0x7fffffffu));
+        xyzz_madd(acc, pt, (e >> 31) != 0);
+    }
+    xyzz_store(partial + (uint64_t)col * partial_stride + s, acc);
+}
+
+// One CTA per column: running-sum reduction over bucket ranges, tree reduction, affine output.
+__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(uint32_t c, const uint32_t* __restrict__ seg_off,
+                                                            const g1_xyzz* __restrict__ partial,
+                                                            uint64_t partial_stride, g1_affine* out) {
+    __shared__ g1_xyzz red[RED_THREADS];
+    const uint32_t NB = 1u << (c - 1);
+    const uint32_t col = blockIdx.x, tid = threadIdx.x;
+    const uint32_t* soff = seg_off + (size_t)col * (NB + 1);
+    const g1_xyzz* part = partial + (uint64_t)col * partial_stride;
+    const uint32_t G = (NB + RED_THREADS - 1) / RED_THREADS;
+    const uint32_t lo = tid * G;
+    const uint32_t hi = min(lo + G, NB);
+    g1_xyzz running = xyzz_identity(), acc = xyzz_identity();
+    for (uint32_t b = hi; b-- > lo;) {
+        uint32_t s1 = soff[b + 1];
+        for (uint32_t s = soff[b]; s < s1; s++) xyzz_add(running, xyzz_load(part + s));
+        xyzz_add(acc, running);
+    }
+    // bucket b carries weight b+1: sum_b (b+1) B_b = acc + lo * running
+    if (lo < NB && lo) {
+        g1_xyzz t = xyzz_identity();
+        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+            t = xyzz_dbl(t);
+            if ((lo >> bit) & 1) xyzz_add(t, running);
+        }
+        xyzz_add(acc, t);
+    }
+    xyzz_store(&red[tid], acc);
+    __syncthreads();
+    for (uint32_t stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
+        if (tid < stride) {
+            g1_xyzz a = xyzz_load(&red[tid]);
+            xyzz_add(a, xyzz_load(&red[tid + stride]));
+            xyzz_store(&red[tid], a);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) affine_store(out + col, xyzz_to_affine(xyzz_load(&red[0])));
+}
+
+static uint32_t pick_window(uint32_t log_n) {
+    uint32_t c = log_n;                 // buckets ~ n/2: balances n*W additions against bucket reduction
+    if (c < 4) c = 4;
+    if (c > 15) c = 15;
+    return c;
+}
+
+int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n) {
+    MsmBasis& B = ctx->basis[which];
+    if (B.table) { ZK_CUDA(ctx, cudaFree(B.table)); B.table = nullptr; B.loaded = false; }
+    B.log_n = log_n;
+    B.c = pick_window(log_n);
+    B.W = (255 + B.c - 1) / B.c;
+    size_t n = (size_t)1 << log_n;
+    if (n * B.W >= (1ull << 31)) return fail(ctx, ZKFHE_ERR_ARG, "msm: n*W=%zu does not fit 31 bits", n * B.W);
+    ZK_CUDA(ctx, cudaMalloc(&B.table, n * B.W * sizeof(g1_affine)));
+    k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, B.table, (uint32_t)n, B.c, B.W);
+    ZK_CHECK_LAUNCH(ctx);
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B.loaded = true;
+    return ZKFHE_OK;
+}
+
+int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log_n, uint32_t batch, int which,
+            g1_affine* d_out) {
+    if (which < 0 || which > 1) return fail(ctx, ZKFHE_ERR_ARG, "msm: basis must be 0 or 1");
+    MsmBasis& B = ctx->basis[which];
+    if (!B.loaded) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
+    if (log_n != B.log_n) return fail(ctx, ZKFHE_ERR_ARG, "msm: log_n=%u but SRS has k=%u", log_n, B.log_n);
+    if (batch == 0) return ZKFHE_OK;
+    const uint32_t n = 1u << log_n, c = B.c, W = B.W, NB = 1u << (c - 1);
+    const uint64_t max_refs = (uint64_t)n * W;
+    const uint64_t max_segs = NB + (max_refs + SEG - 1) / SEG;
+    // bound the workspace: process the batch in chunks
+    const uint64_t per_col = max_refs * 4 + max_segs * sizeof(g1_xyzz) + 2ull * (NB + 1) * 4;
+    uint32_t chunk = (uint32_t)((3ull << 30) / per_col);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk > 65535) chunk = 65535;
+    uint32_t *boff, *soff, *sorted;
+    g1_xyzz* partial;
+    ZK_TRY(ws_get(ctx, "msm_boff", (size_t)chunk * (NB + 1) * 4, (void**)&boff));
+    ZK_TRY(ws_get(ctx, "msm_soff", (size_t)chunk * (NB + 1) * 4, (void**)&soff));
+    ZK_TRY(ws_get(ctx, "msm_sorted", (size_t)chunk * max_refs * 4, (void**)&sorted));
+    ZK_TRY(ws_get(ctx, "msm_partial", (size_t)chunk * max_segs * sizeof(g1_xyzz), (void**)&partial));
+    size_t smem = (size_t)NB * 4;
+    if (smem > 48 * 1024)
+        ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->ev_used = 0;
+    for (uint32_t done = 0; done < batch; done += chunk) {
+        uint32_t nb = batch - done < chunk ? batch - done : chunk;
+        const fr_t* sc = d_scalars + (uint64_t)done * stride;
+        k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(timed_begin(ctx));
+        dim3 grid((uint32_t)((max_segs + 127) / 128), nb);
+        k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, boff, soff, sorted, max_refs, partial, max_segs);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(timed_end(ctx));
+        k_msm_reduce<<<nb, RED_THREADS, 0, ctx->stream>>>(c, soff, partial, max_segs, d_out + done);
+        ZK_CHECK_LAUNCH(ctx);
+    }
+    return ZKFHE_OK;
+}
+
+}  // namespace zkfhe
