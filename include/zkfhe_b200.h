@@ -58,7 +58,8 @@ int zkfhe_init(int device, zkfhe_ctx** ctx);
 void zkfhe_destroy(zkfhe_ctx* ctx);
 const char* zkfhe_last_error(const zkfhe_ctx* ctx);
 const char* zkfhe_version(void);
-/* Run all subsequent work on `cuda_stream` (a cudaStream_t); NULL = the context's own stream. */
+/* Run all subsequent work on `cuda_stream` (a cudaStream_t; NULL is the CUDA legacy default
+ * stream).  Until this is called the context uses a private non-blocking stream. */
 int zkfhe_set_stream(zkfhe_ctx* ctx, void* cuda_stream);
 int zkfhe_sync(zkfhe_ctx* ctx);
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */
@@ -92,6 +93,105 @@ int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t
 /* out[b] = sum_i scalars[b][i] * basis[i], b < batch; scalars are batch x 2^k Fr. */
 int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int basis, uint8_t* h_out_affine);
 int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, uint8_t* d_out_affine);
+
+/* ---- stage (1a): off-circuit polynomial arithmetic ----------------------------------------
+ * Device-resident mirror of `zk_fhe::poly::Poly` (src/poly.rs:9-13): `len` plain integer
+ * coefficients (u256), big-endian, plus the `max_bits` bookkeeping.  All calls are
+ * asynchronous on the context's stream; data-dependent `assert!`s of the reference are
+ * recorded in a sticky status word that zkfhe_status() reads back (ZKFHE_ERR_ASSERT). */
+typedef struct zkfhe_poly zkfhe_poly;
+/* Poly::from_string after decimal parsing (poly.rs:21-40): asserts coeff <= modulus (:28). */
+int zkfhe_poly_from_u64(zkfhe_ctx* ctx, const uint64_t* h_coeffs, uint32_t len, uint64_t modulus, zkfhe_poly** out);
+/* Poly::from_big_int (poly.rs:47-59): asserts bits(coeff) <= max_bits (:51). */
+int zkfhe_poly_from_u256(zkfhe_ctx* ctx, const uint64_t* h_coeffs_u256, uint32_t len, uint64_t max_bits, zkfhe_poly** out);
+/* Poly::mul (poly.rs:75-103): exact integer product of two equal-degree polynomials, computed
+ * as an NTT over Fr (exact while max_bits_a + max_bits_b + log2_ceil(len) < 254, else
+ * ZKFHE_ERR_OVERFLOW -- the bound the circuit itself asserts at src/poly_chip.rs:90-94). */
+int zkfhe_poly_mul(zkfhe_ctx* ctx, const zkfhe_poly* a, const zkfhe_poly* b, zkfhe_poly** out);
+/* Poly::reduce_by_modulus (poly.rs:180-191). */
+int zkfhe_poly_reduce_by_modulus(zkfhe_ctx* ctx, const zkfhe_poly* a, uint64_t modulus, zkfhe_poly** out);
+/* Poly::divide_by_cyclo (poly.rs:113-177) for cyclo = x^N + 1 (the documented assumption, :111);
+ * quotient has N+1, remainder 2N+1 coefficients; the all-zero shortcut (:118-123) is kept. */
+int zkfhe_poly_divide_by_cyclo(zkfhe_ctx* ctx, const zkfhe_poly* a, const zkfhe_poly* cyclo, uint64_t modulus,
+                               zkfhe_poly** quotient, zkfhe_poly** remainder);
+uint32_t zkfhe_poly_len(const zkfhe_poly* p);
+uint64_t zkfhe_poly_max_bits(const zkfhe_poly* p);
+int zkfhe_poly_download(zkfhe_ctx* ctx, const zkfhe_poly* p, uint64_t* h_out_u256);
+void zkfhe_poly_free(zkfhe_poly* p);
+/* Synchronise and return the sticky status (ZKFHE_OK or the first recorded reference assert). */
+int zkfhe_status(zkfhe_ctx* ctx);
+
+/* ---- stage (1b): in-circuit witness generation --------------------------------------------
+ * Mirror of `zk_fhe::poly_chip::PolyChip<F>` (src/poly_chip.rs:19-23) over halo2-base
+ * `Context`s: a witness object owns the flat advice vector of each context
+ * (context 0: phase-0 gate, 1: phase-1 gate, 2: phase-1 RLC) and the lookup-cell list, all
+ * resident in HBM.  Each chip call assigns exactly the cells the CPU builder assigns, in the
+ * same order, by one kernel launch over the coefficients. */
+typedef struct zkfhe_witness zkfhe_witness;
+typedef struct {
+    uint32_t ctx_id;    /* which Context holds the cells                                 */
+    uint32_t stride;    /* coefficient i lives at advice[base + i * stride]              */
+    uint64_t base;
+    uint32_t len;       /* degree + 1                                                     */
+    uint32_t reserved;
+    uint64_t max_num_bits;
+} zkfhe_assigned_poly;  /* = PolyChip { assigned_coefficients, max_num_bits, degree }     */
+typedef struct {
+    uint32_t ctx_id;
+    uint32_t reserved;
+    uint64_t offset;
+} zkfhe_cell;           /* = AssignedValue                                                */
+
+int zkfhe_witness_new(zkfhe_ctx* ctx, uint32_t lookup_bits, zkfhe_witness** out);
+void zkfhe_witness_free(zkfhe_witness* w);
+int zkfhe_witness_reset(zkfhe_witness* w);   /* keep the buffers, forget the cells (next proof) */
+/* PolyChip::from_poly (poly_chip.rs:27-42) */
+int zkfhe_chip_from_poly(zkfhe_witness* w, uint32_t ctx_id, const zkfhe_poly* p, zkfhe_assigned_poly* out);
+/* ctx.load_constant (examples/bfv.rs:115) */
+int zkfhe_chip_load_constant(zkfhe_witness* w, uint32_t ctx_id, uint64_t value, zkfhe_cell* out);
+/* PolyChip::to_public (poly_chip.rs:58-62) */
+int zkfhe_chip_to_public(zkfhe_witness* w, const zkfhe_assigned_poly* p);
+/* The phase-0 challenge gamma (Fr, Montgomery) used by RlcChip in phase 1 (examples/bfv.rs:92-98) */
+int zkfhe_chip_set_challenge(zkfhe_witness* w, const uint8_t* h_gamma_fr);
+/* PolyChip::constrain_mul (poly_chip.rs:81-116) */
+int zkfhe_chip_constrain_mul(zkfhe_witness* w, uint32_t ctx_gate, uint32_t ctx_rlc, const zkfhe_assigned_poly* a,
+                             const zkfhe_assigned_poly* b, const zkfhe_assigned_poly* c);
+/* PolyChip::add (poly_chip.rs:122-144) */
+int zkfhe_chip_add(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a, const zkfhe_assigned_poly* b,
+                   zkfhe_assigned_poly* out);
+/* PolyChip::scalar_mul (poly_chip.rs:150-174); scalar_value is the constant held by `scalar` */
+int zkfhe_chip_scalar_mul(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a, const zkfhe_cell* scalar,
+                          uint64_t scalar_value, zkfhe_assigned_poly* out);
+/* PolyChip::reduce_by_cyclo (poly_chip.rs:183-223) */
+int zkfhe_chip_reduce_by_cyclo(zkfhe_witness* w, uint32_t ctx_gate, uint32_t ctx_rlc, const zkfhe_assigned_poly* self,
+                               const zkfhe_assigned_poly* cyclo, const zkfhe_assigned_poly* quotient,
+                               const zkfhe_assigned_poly* quotient_times_cyclo, const zkfhe_assigned_poly* remainder,
+                               uint64_t modulus, zkfhe_assigned_poly* out);
+/* PolyChip::reduce_by_modulo (poly_chip.rs:226-252) */
+int zkfhe_chip_reduce_by_modulo(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a, uint64_t modulus,
+                                zkfhe_assigned_poly* out);
+/* PolyChip::constrain_equality (poly_chip.rs:255-264) */
+int zkfhe_chip_constrain_equality(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a,
+                                  const zkfhe_assigned_poly* b);
+/* PolyChip::constrain_coefficients_in_range (poly_chip.rs:270-317) */
+int zkfhe_chip_constrain_coefficients_in_range(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a,
+                                               uint64_t z, uint64_t y);
+/* PolyChip::constrain_from_distribution_chi_key (poly_chip.rs:320-354) */
+int zkfhe_chip_constrain_from_distribution_chi_key(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assigned_poly* a,
+                                                   uint64_t z);
+/* PolyChip::constrain_coefficients_in_modulus_field (poly_chip.rs:357-366) */
+int zkfhe_chip_constrain_coefficients_in_modulus_field(zkfhe_witness* w, uint32_t ctx_gate,
+                                                       const zkfhe_assigned_poly* a, uint64_t modulus);
+/* PolyChip::safe_trim_leading_zeroes (poly_chip.rs:374-399) */
+int zkfhe_chip_safe_trim_leading_zeroes(zkfhe_witness* w, const zkfhe_assigned_poly* a, uint32_t degree,
+                                        zkfhe_assigned_poly* out);
+/* Sizes so far: advice cells per context, lookup cells, public instances. */
+int zkfhe_witness_counts(const zkfhe_witness* w, uint64_t advice_cells[3], uint64_t* lookup_cells, uint64_t* instances);
+/* Copy a flat vector to the host as Fr (Montgomery): which = 0,1,2 advice of that context,
+ * 3 = lookup cells (creation order), 4 = instance values. */
+int zkfhe_witness_download(zkfhe_witness* w, uint32_t which, uint8_t* h_out_fr);
+/* Device address of the same vectors (valid until the next chip call grows the buffer). */
+int zkfhe_witness_device_ptr(zkfhe_witness* w, uint32_t which, uint8_t** d_ptr);
 
 /* ---- timing hook -------------------------------------------------------------------------
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last

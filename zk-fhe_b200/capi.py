@@ -54,7 +54,60 @@ _SIGNATURES = {
     "zkfhe_msm_g1": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_msm_g1_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_last_kernel_ms": (_c.c_float, [_c.c_void_p]),
+    # stage (1a): Poly
+    "zkfhe_poly_from_u64": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_from_u256": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_mul": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_reduce_by_modulus": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_divide_by_cyclo": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64,
+                                              _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_len": (_c.c_uint32, [_c.c_void_p]),
+    "zkfhe_poly_max_bits": (_c.c_uint64, [_c.c_void_p]),
+    "zkfhe_poly_download": (_c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    "zkfhe_poly_free": (None, [_c.c_void_p]),
+    "zkfhe_status": (_c.c_int, [_c.c_void_p]),
+    # stage (1b): PolyChip witness
+    "zkfhe_witness_new": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_witness_free": (None, [_c.c_void_p]),
+    "zkfhe_witness_reset": (_c.c_int, [_c.c_void_p]),
+    "zkfhe_chip_from_poly": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p]),
+    "zkfhe_chip_load_constant": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_void_p]),
+    "zkfhe_chip_to_public": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "zkfhe_chip_set_challenge": (_c.c_int, [_c.c_void_p, _u8p]),
+    "zkfhe_chip_constrain_mul": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "zkfhe_chip_add": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "zkfhe_chip_scalar_mul": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "zkfhe_chip_reduce_by_cyclo": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_void_p,
+                                              _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "zkfhe_chip_reduce_by_modulo": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "zkfhe_chip_constrain_equality": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p]),
+    "zkfhe_chip_constrain_coefficients_in_range": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64, _c.c_uint64]),
+    "zkfhe_chip_constrain_from_distribution_chi_key": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64]),
+    "zkfhe_chip_constrain_coefficients_in_modulus_field": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64]),
+    "zkfhe_chip_safe_trim_leading_zeroes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p]),
+    "zkfhe_witness_counts": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
+    "zkfhe_witness_download": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p]),
+    "zkfhe_witness_device_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
 }
+
+
+class AssignedPoly(_c.Structure):
+    """zkfhe_assigned_poly (= PolyChip { assigned_coefficients, max_num_bits, degree })."""
+    _fields_ = [("ctx_id", _c.c_uint32), ("stride", _c.c_uint32), ("base", _c.c_uint64), ("len", _c.c_uint32),
+                ("reserved", _c.c_uint32), ("max_num_bits", _c.c_uint64)]
+
+
+class Cell(_c.Structure):
+    """zkfhe_cell (= AssignedValue)."""
+    _fields_ = [("ctx_id", _c.c_uint32), ("reserved", _c.c_uint32), ("offset", _c.c_uint64)]
+
+
+FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def fr_mont_bytes(x):
+    """Canonical int -> the 32-byte ABI layout of an Fr element (Montgomery, R = 2^256)."""
+    return bytearray((((int(x) % FR_MODULUS) << 256) % FR_MODULUS).to_bytes(32, "little"))
 
 
 def load_library(build_if_missing=True):
@@ -127,6 +180,10 @@ class Context:
 
     def sync(self):
         self._check(self.lib.zkfhe_sync(self.h))
+
+    def status(self):
+        """Synchronise and raise if a data-dependent reference assert fired on the device."""
+        self._check(self.lib.zkfhe_status(self.h))
 
     def launch_count(self):
         return int(self.lib.zkfhe_launch_count(self.h))

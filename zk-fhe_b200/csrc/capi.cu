@@ -135,14 +135,9 @@ const char* zkfhe_last_error(const zkfhe_ctx* ctx) { return ctx ? ctx->err.c_str
 int zkfhe_set_stream(zkfhe_ctx* ctx, void* cuda_stream) {
     if (!ctx) return ZKFHE_ERR_ARG;
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (cuda_stream == nullptr && !ctx->own_stream) {
-        ZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    } else if (cuda_stream != nullptr) {
-        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-        ctx->stream = (cudaStream_t)cuda_stream;
-        ctx->own_stream = false;
-    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;     // NULL is the CUDA legacy default stream
+    ctx->own_stream = false;
     return ZKFHE_OK;
 }
 

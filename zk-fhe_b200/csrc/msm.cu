@@ -14,10 +14,11 @@
 //    instead of W.
 //  * Per column: (1) one CTA recodes the scalars into signed c-bit digits and
 //    counting-sorts the (point, sign) references by bucket in shared memory;
-//    (2) buckets are cut into segments of <= SEG references and one thread sums
-//    each segment with mixed XYZZ additions -- witness columns are full of
-//    repeated small values, so bucket sizes are heavily skewed and per-bucket
-//    threads would serialise; (3) one CTA per column folds the segment sums with
+//    (2) the sorted list is cut into fixed slices of SEG references; one thread sums a
+//    slice with mixed XYZZ additions and emits a partial sum at every bucket boundary it
+//    crosses -- witness columns are full of repeated small values, so bucket sizes are
+//    heavily skewed and per-bucket threads would serialise or leave lanes idle;
+//    (3) one CTA per column folds the partial sums with
 //    the running-sum trick, each thread owning a contiguous bucket range, then a
 //    shared-memory tree reduction and a single inversion give the affine point.
 //  * The hot loop (2) gathers 64-byte affine points from the L2-resident table;
@@ -26,7 +27,7 @@
 
 namespace zkfhe {
 
-static constexpr uint32_t SEG = 64;          // max point references summed by one thread
+static constexpr uint32_t SEG = 32;          // point references summed by one thread
 static constexpr uint32_t RED_THREADS = 256; // threads of the per-column reduction CTA
 
 // ---- fixed-base table ---------------------------------------------------------------------
@@ -73,13 +74,13 @@ __device__ __forceinline__ void for_each_digit(const fr_t& s_canon, uint32_t c, 
 }
 
 // One CTA per column: histogram -> exclusive scans -> scatter (counting sort by bucket).
-//   bucket_off[col][NB+1] : start of each bucket in sorted[col]
-//   seg_off[col][NB+1]    : first segment id of each bucket (segments of <= SEG references)
+//   bucket_off[col][NB+1] : start of each bucket in sorted[col]; bucket_off[NB] = number of references
+//   rank[col][NB+1]       : number of non-empty buckets before bucket b
 //   sorted[col][..]       : (w*n + i) | sign<<31, grouped by bucket
 extern __shared__ uint32_t msm_smem[];
 
 __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
-                                                   uint32_t W, uint32_t* bucket_off, uint32_t* seg_off,
+                                                   uint32_t W, uint32_t* bucket_off, uint32_t* rank_out,
                                                    uint32_t* sorted, uint64_t sorted_stride) {
     const uint32_t NB = 1u << (c - 1);
     uint32_t* cnt = msm_smem;                 // [NB] counts, then running cursors
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     const uint32_t col = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const fr_t* sc = scalars + (uint64_t)col * stride;
     uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
-    uint32_t* soff = seg_off + (size_t)col * (NB + 1);
+    uint32_t* rnk = rank_out + (size_t)col * (NB + 1);
     uint32_t* out = sorted + (uint64_t)col * sorted_stride;
 
     for (uint32_t b = tid; b < NB; b += nt) cnt[b] = 0;
@@ -98,15 +99,14 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     }
     __syncthreads();
 
-    // exclusive scan of counts (entries) and of ceil(count/SEG) (segments); NB = per * nt chunks
+    // exclusive scans of the counts (entries) and of the non-empty flags (ranks)
     const uint32_t per = (NB + nt - 1) / nt;
     const uint32_t b0 = tid * per;
     uint32_t sum_e = 0, sum_s = 0;
     for (uint32_t k = 0; k < per; k++) {
         uint32_t b = b0 + k;
-        if (b < NB) { uint32_t v = cnt[b]; sum_e += v; sum_s += (v + SEG - 1) / SEG; }
+        if (b < NB) { uint32_t v = cnt[b]; sum_e += v; sum_s += (v != 0); }
     }
-    // block-wide exclusive scan of (sum_e, sum_s)
     uint32_t lane = tid & 31, wid = tid >> 5;
     uint32_t inc_e = sum_e, inc_s = sum_s;
     for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
         if (b < NB) {
             uint32_t v = cnt[b];
             boff[b] = run_e;
-            soff[b] = run_s;
+            rnk[b] = run_s;
             cnt[b] = run_e;            // becomes the scatter cursor
             run_e += v;
-            run_s += (v + SEG - 1) / SEG;
+            run_s += (v != 0);
         }
     }
-    if (tid == nt - 1) { boff[NB] = run_e; soff[NB] = run_s; }
+    if (tid == nt - 1) { boff[NB] = run_e; rnk[NB] = run_s; }
     __syncthreads();
 
     for (uint32_t i = tid; i < n; i += nt) {
@@ -154,53 +154,68 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     }
 }
 
-// One thread per segment: sum <= SEG signed table points (mixed XYZZ adds).
+// Thread t of a column sums references [t*SEG, (t+1)*SEG) of the bucket-sorted list with mixed XYZZ
+// additions -- every lane of a warp does the same number of additions whatever the bucket sizes --
+// and writes one partial sum per bucket it touches to slot rank[b] + t.  Slots are strictly
+// increasing along the list, so they never collide; bucket b's partials are exactly the slots
+// rank[b] + t for t in [boff[b]/SEG, (boff[b+1]-1)/SEG].
 __global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restrict__ table, uint32_t c,
                                                         const uint32_t* __restrict__ bucket_off,
-                                                        const uint32_t* __restrict__ seg_off,
+                                                        const uint32_t* __restrict__ rank_in,
                                                         const uint32_t* __restrict__ sorted, uint64_t sorted_stride,
                                                         g1_xyzz* partial, uint64_t partial_stride) {
     const uint32_t NB = 1u << (c - 1);
     const uint32_t col = blockIdx.y;
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
-    const uint32_t* soff = seg_off + (size_t)col * (NB + 1);
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= soff[NB]) return;
-    // bucket b with soff[b] <= s < soff[b+1]  (empty buckets have soff[b] == soff[b+1])
-    uint32_t lo = 0, hi = NB;               // invariant: soff[lo] <= s < soff[hi]
+    const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = boff[NB];
+    const uint32_t k0 = t * SEG;
+    if (k0 >= total) return;
+    const uint32_t k1 = min(k0 + SEG, total);
+    uint32_t lo = 0, hi = NB;               // largest b with boff[b] <= k0  (then boff[b+1] > k0)
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (soff[mid] <= s) lo = mid; else hi = mid;
+        if (boff[mid] <= k0) lo = mid; else hi = mid;
     }
-    const uint32_t b = lo;
-    const uint32_t start = boff[b] + (s - soff[b]) * SEG;
-    const uint32_t end = min(start + SEG, boff[b + 1]);
+    uint32_t b = lo, next = boff[b + 1];
     const uint32_t* ref = sorted + (uint64_t)col * sorted_stride;
+    g1_xyzz* out = partial + (uint64_t)col * partial_stride + t;
     g1_xyzz acc = xyzz_identity();
-    for (uint32_t k = start; k < end; k++) {
+    for (uint32_t k = k0; k < k1; k++) {
+        if (k == next) {
+            xyzz_store(out + rnk[b], acc);
+            acc = xyzz_identity();
+            do { b++; next = boff[b + 1]; } while (next == k);
+        }
         uint32_t e = ref[k];
         g1_affine pt = affine_load(table + (e & 0x7fffffffu));
         xyzz_madd(acc, pt, (e >> 31) != 0);
     }
-    xyzz_store(partial + (uint64_t)col * partial_stride + s, acc);
+    xyzz_store(out + rnk[b], acc);
 }
 
 // One CTA per column: running-sum reduction over bucket ranges, tree reduction, affine output.
-__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(uint32_t c, const uint32_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(uint32_t c, const uint32_t* __restrict__ bucket_off,
+                                                            const uint32_t* __restrict__ rank_in,
                                                             const g1_xyzz* __restrict__ partial,
                                                             uint64_t partial_stride, g1_affine* out) {
     __shared__ g1_xyzz red[RED_THREADS];
     const uint32_t NB = 1u << (c - 1);
     const uint32_t col = blockIdx.x, tid = threadIdx.x;
-    const uint32_t* soff = seg_off + (size_t)col * (NB + 1);
+    const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
     const g1_xyzz* part = partial + (uint64_t)col * partial_stride;
     const uint32_t G = (NB + RED_THREADS - 1) / RED_THREADS;
     const uint32_t lo = tid * G;
     const uint32_t hi = min(lo + G, NB);
     g1_xyzz running = xyzz_identity(), acc = xyzz_identity();
     for (uint32_t b = hi; b-- > lo;) {
-        uint32_t s1 = soff[b + 1];
-        for (uint32_t s = soff[b]; s < s1; s++) xyzz_add(running, xyzz_load(part + s));
+        uint32_t e0 = boff[b], e1 = boff[b + 1];
+        if (e1 > e0) {
+            uint32_t r = rnk[b];
+            for (uint32_t t = e0 / SEG; t <= (e1 - 1) / SEG; t++) xyzz_add(running, xyzz_load(part + r + t));
+        }
         xyzz_add(acc, running);
     }
     // bucket b carries weight b+1: sum_b (b+1) B_b = acc + lo * running
@@ -257,7 +272,8 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     if (batch == 0) return ZKFHE_OK;
     const uint32_t n = 1u << log_n, c = B.c, W = B.W, NB = 1u << (c - 1);
     const uint64_t max_refs = (uint64_t)n * W;
-    const uint64_t max_segs = NB + (max_refs + SEG - 1) / SEG;
+    const uint64_t max_thr = (max_refs + SEG - 1) / SEG;     // accumulate threads per column
+    const uint64_t max_segs = NB + max_thr;                  // partial slots: rank[b] + t
     // bound the workspace: process the batch in chunks
     const uint64_t per_col = max_refs * 4 + max_segs * sizeof(g1_xyzz) + 2ull * (NB + 1) * 4;
     uint32_t chunk = (uint32_t)((3ull << 30) / per_col);
@@ -280,11 +296,11 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_begin(ctx));
-        dim3 grid((uint32_t)((max_segs + 127) / 128), nb);
+        dim3 grid((uint32_t)((max_thr + 127) / 128), nb);
         k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, boff, soff, sorted, max_refs, partial, max_segs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
-        k_msm_reduce<<<nb, RED_THREADS, 0, ctx->stream>>>(c, soff, partial, max_segs, d_out + done);
+        k_msm_reduce<<<nb, RED_THREADS, 0, ctx->stream>>>(c, boff, soff, partial, max_segs, d_out + done);
         ZK_CHECK_LAUNCH(ctx);
     }
     return ZKFHE_OK;
