@@ -41,8 +41,9 @@ NTT_BYTES_PER_ELEM = 64          # 32 B read + 32 B write
 
 
 def synth_columns(rng, count):
-    """Synthetic scalars with the value mix of real columns: advice/lookup columns hold small
-    values with a sprinkling of full-size ones; grand-product and quotient columns are full-size."""
+    """Synthetic scalars (CANONICAL 4xu64 integers; convert to Montgomery before use) with the
+    value mix of real columns: advice/lookup columns hold small values with a sprinkling of
+    full-size ones; grand-product and quotient columns are full-size."""
     cols = np.zeros((count, N_ROWS, 4), np.uint64)
     full = rng.integers(0, 1 << 63, size=(count, N_ROWS, 4), dtype=np.uint64)
     full[:, :, 3] &= np.uint64((1 << 60) - 1)
@@ -114,6 +115,7 @@ def cpu_reference_arm(steps, warmup, threads=0):
     _, gl = cbind.srs(K, 0x5EED5EED5EED, want_g=False)
     s_msm, s_ntt = 4, 8
     cols = synth_columns(rng, C_MSM)
+    cbind.lib().orc_to_mont_array(0, cols.ctypes.data, cols.ctypes.data, cols.shape[0])
     pick = [0, C_ADVICE - 1, C_ADVICE + C_LOOKUP_PERM + 1, C_MSM - 1]        # 2 small-valued + 2 full-size columns
     msm_in = np.ascontiguousarray(np.concatenate([cols[c * N_ROWS:(c + 1) * N_ROWS] for c in pick]))
     ntt_in = np.ascontiguousarray(cols[-s_ntt * N_ROWS:])
@@ -176,7 +178,6 @@ def main():
     import torch.distributed as dist
 
     import zk_fhe_b200
-    from oracle import cbind     # SRS generation only (test tau); never on the timed path
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -186,12 +187,13 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
-    _, gl = cbind.srs(K, 0x5EED5EED5EED, want_g=False)
-    ctx.load_srs(K, g=None, g_lagrange=gl)
+    ctx.srs_setup(K, 0x5EED5EED5EED)                 # insecure test SRS, generated on the GPU
     rng = np.random.default_rng(1234 + rank)
     host_cols = synth_columns(rng, C_MSM)
-    h_scal = torch.from_numpy(host_cols.view(np.int64)).pin_memory()
-    d_scal = h_scal.to(dev)
+    d_scal = torch.from_numpy(host_cols.view(np.int64)).to(dev)
+    ctx.fr_convert_dev(d_scal.data_ptr(), d_scal.shape[0], True)       # canonical -> Montgomery (ABI layout)
+    torch.cuda.synchronize()
+    h_scal = d_scal.cpu().pin_memory()
     d_points = torch.empty((C_MSM, 8), dtype=torch.int64, device=dev)
     h_points = torch.empty((C_MSM, 8), dtype=torch.int64).pin_memory()
     d_coef = torch.empty((C_NTT * N_ROWS, 4), dtype=torch.int64, device=dev)

@@ -90,6 +90,13 @@ int zkfhe_coeff_to_extended_dev(zkfhe_ctx* ctx, const uint8_t* d_coeffs, uint32_
  * zkfhe_load_srs uploads both bases (n = 2^k points each) and builds the resident
  * fixed-base window tables; `basis` selects 0 = g (coefficient form), 1 = g_lagrange. */
 int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t* h_g_lagrange);
+/* Test SRS, the shape of halo2 `ParamsKZG::setup` that halo2-scaffold's `gen_srs(k)` falls back to
+ * when no params file exists: g[i] = tau^i * G1, g_lagrange[i] = l_i(tau) * G1, computed on the
+ * GPU from an explicit tau (Fr, Montgomery) and loaded as by zkfhe_load_srs.  The bases are also
+ * copied to the host when the output pointers are non-NULL (n x 64 bytes each).  INSECURE. */
+int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t* h_g_out, uint8_t* h_g_lagrange_out);
+/* In place: canonical 256-bit integers -> Montgomery Fr (to_montgomery = 1) or back (0). */
+int zkfhe_fr_convert_dev(zkfhe_ctx* ctx, uint8_t* d_data, uint64_t count, int to_montgomery);
 /* out[b] = sum_i scalars[b][i] * basis[i], b < batch; scalars are batch x 2^k Fr. */
 int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int basis, uint8_t* h_out_affine);
 int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, uint8_t* d_out_affine);

@@ -145,6 +145,10 @@ EXPORT void orc_field_inv(int which, uint64_t* r, const uint64_t* a) { f_inv(whi
 EXPORT void orc_to_mont(int which, uint64_t* r, const uint64_t* a) { f_to_mont(which ? &FQ : &FR, (fe*)r, (const fe*)a); }
 EXPORT void orc_from_mont(int which, uint64_t* r, const uint64_t* a) { f_from_mont(which ? &FQ : &FR, (fe*)r, (const fe*)a); }
 
+EXPORT void orc_to_mont_array(int which, const uint64_t* in, uint64_t* out, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) f_to_mont(which ? &FQ : &FR, (fe*)(out + 4 * i), (const fe*)(in + 4 * i));
+}
+
 /* ---- NTT (halo2 best_fft shape) ---------------------------------------------------------- */
 static uint32_t bitrev32(uint32_t x, uint32_t bits) {
     uint32_t r = 0;

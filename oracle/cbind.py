@@ -29,6 +29,7 @@ def lib():
         L.orc_field_inv.argtypes = [ci, vp, vp]
         L.orc_to_mont.argtypes = [ci, vp, vp]
         L.orc_from_mont.argtypes = [ci, vp, vp]
+        L.orc_to_mont_array.argtypes = [ci, vp, vp, u64]
         L.orc_ntt.argtypes = [vp, u32, u32, ci, ci, ci]
         L.orc_msm.argtypes = [vp, vp, u32, u32, vp, ci]
         L.orc_srs.argtypes = [u32, vp, vp, vp, ci]

@@ -180,6 +180,34 @@ def test_msm_k13_witness_like_columns_match_oracle(ctx):
     assert ps == curve.g1_add(_pt(got[0]), _pt(got[1]))
 
 
+def test_srs_setup_on_gpu_matches_oracle(ctx):
+    """zkfhe_srs_setup (ParamsKZG::setup shape) vs the oracle's g[i] = tau^i G, g_lagrange[i] = l_i(tau) G."""
+    import zk_fhe_b200
+    k, tau = 7, 0x1F2E3D4C5B6A79880123456789
+    c2 = zk_fhe_b200.Context(0)
+    g, gl = c2.srs_setup(k, tau, want_host_copy=True)
+    og, ogl = cbind.srs(k, tau)
+    assert g == og.tobytes() and gl == ogl.tobytes()
+    rng = np.random.default_rng(3)
+    sc = random_fr_mont(rng, 1 << k)
+    for basis, bases in ((0, og), (1, ogl)):
+        assert c2.msm_g1(sc, 1, basis=basis) == cbind.msm(sc, bases, 1 << k, 1).tobytes()
+    c2.close()
+
+
+def test_fr_convert_roundtrip(ctx):
+    import torch
+    vals = [0, 1, 2, field.R_MOD - 1, 1 << 200, 536870909]
+    canon = cbind.ints_to_u64x4(vals)
+    d = torch.from_numpy(canon.view(np.int64)).cuda()
+    ctx.fr_convert_dev(d.data_ptr(), len(vals), True)
+    ctx.sync()
+    assert mont_array_to_fr(d.cpu().numpy().view(np.uint64)) == vals
+    ctx.fr_convert_dev(d.data_ptr(), len(vals), False)
+    ctx.sync()
+    assert np.array_equal(d.cpu().numpy().view(np.uint64), canon)
+
+
 def test_msm_errors(ctx):
     import zk_fhe_b200
     c2 = zk_fhe_b200.Context(0)

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "zkfhe_ntt_fr_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
     "zkfhe_coeff_to_extended_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _u8p, _c.c_uint32, _c.c_uint32]),
     "zkfhe_load_srs": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p, _u8p]),
+    "zkfhe_srs_setup": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p, _u8p, _u8p]),
+    "zkfhe_fr_convert_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint64, _c.c_int]),
     "zkfhe_msm_g1": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_msm_g1_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_last_kernel_ms": (_c.c_float, [_c.c_void_p]),
@@ -211,6 +213,18 @@ class Context:
     def load_srs(self, k, g=None, g_lagrange=None):
         self._check(self.lib.zkfhe_load_srs(self.h, k, _addr(g), _addr(g_lagrange)))
         self.srs_k = k
+
+    def srs_setup(self, k, tau, want_host_copy=False):
+        """Insecure test SRS from an explicit tau (canonical int); returns (g, g_lagrange) bytes if asked."""
+        t = fr_mont_bytes(tau)
+        g = bytearray(64 << k) if want_host_copy else None
+        gl = bytearray(64 << k) if want_host_copy else None
+        self._check(self.lib.zkfhe_srs_setup(self.h, k, _addr(t), _addr(g), _addr(gl)))
+        self.srs_k = k
+        return (bytes(g), bytes(gl)) if want_host_copy else None
+
+    def fr_convert_dev(self, d_ptr, count, to_montgomery=True):
+        self._check(self.lib.zkfhe_fr_convert_dev(self.h, d_ptr, count, int(to_montgomery)))
 
     def msm_g1(self, scalars, batch, basis=1):
         out = bytearray(64 * batch)

@@ -2,6 +2,7 @@
 // staging and the on-device self test.  Compute lives in ntt.cu / msm.cu /
 // witness.cu; nothing here falls back to the CPU.
 #include <new>
+#include <cstring>
 #include "common.cuh"
 
 using namespace zkfhe;
@@ -219,6 +220,32 @@ int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t
     }
     ctx->srs_k = k;
     return ZKFHE_OK;
+}
+
+int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t* h_g_out, uint8_t* h_g_lagrange_out) {
+    if (!ctx || !h_tau_fr) return fail(ctx, ZKFHE_ERR_ARG, "srs_setup: null pointer");
+    if (k < 1 || k > 22) return fail(ctx, ZKFHE_ERR_ARG, "srs_setup: k=%u out of range [1,22]", k);
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = ((size_t)1 << k) * sizeof(g1_affine);
+    g1_affine* d;
+    ZK_TRY(ws_get(ctx, "srs_setup", 2 * bytes, (void**)&d));
+    fr_t tau;
+    memcpy(&tau, h_tau_fr, 32);
+    ZK_TRY(srs_setup(ctx, k, tau, d, d + ((size_t)1 << k)));
+    ZK_TRY(msm_load_basis(ctx, 0, d, k));
+    ZK_TRY(msm_load_basis(ctx, 1, d + ((size_t)1 << k), k));
+    ctx->srs_k = k;
+    if (h_g_out) ZK_CUDA(ctx, cudaMemcpyAsync(h_g_out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_g_lagrange_out)
+        ZK_CUDA(ctx, cudaMemcpyAsync(h_g_lagrange_out, d + ((size_t)1 << k), bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_fr_convert_dev(zkfhe_ctx* ctx, uint8_t* d_data, uint64_t count, int to_montgomery) {
+    if (!ctx || (!d_data && count)) return fail(ctx, ZKFHE_ERR_ARG, "fr_convert: null pointer");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return fr_convert(ctx, reinterpret_cast<fr_t*>(d_data), count, to_montgomery);
 }
 
 int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, uint8_t* d_out_affine) {

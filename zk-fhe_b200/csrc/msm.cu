@@ -27,8 +27,7 @@
 
 namespace zkfhe {
 
-static constexpr uint32_t SEG = 32;          // point references summed by one thread
-static constexpr uint32_t RED_THREADS = 256; // threads of the per-column reduction CTA
+static constexpr uint32_t SEG = 64;          // point references summed by one thread
 
 // ---- fixed-base table ---------------------------------------------------------------------
 __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint32_t n, uint32_t c, uint32_t W) {
@@ -195,49 +194,130 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restr
     xyzz_store(out + rnk[b], acc);
 }
 
-// One CTA per column: running-sum reduction over bucket ranges, tree reduction, affine output.
-__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(uint32_t c, const uint32_t* __restrict__ bucket_off,
-                                                            const uint32_t* __restrict__ rank_in,
-                                                            const g1_xyzz* __restrict__ partial,
-                                                            uint64_t partial_stride, g1_affine* out) {
-    __shared__ g1_xyzz red[RED_THREADS];
+// Out-of-line point addition for the reduction kernels: they are latency-bound and call it from
+// several places, so keeping one copy keeps them inside the instruction cache.
+__device__ __noinline__ void xyzz_add_ni(g1_xyzz& acc, const g1_xyzz& p) { xyzz_add(acc, p); }
+
+// Reduction, level 1: one thread per group of FOLD consecutive buckets.  Folds the partial sums of
+// each bucket and runs the running-sum trick inside the group:
+//   S_g = sum_b B_b,   A_g = sum_b (b - lo + 1) B_b      (so sum_b (b+1) B_b = A_g + lo * S_g)
+__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, const uint32_t* __restrict__ bucket_off,
+                                                  const uint32_t* __restrict__ rank_in,
+                                                  const g1_xyzz* __restrict__ partial, uint64_t partial_stride,
+                                                  g1_xyzz* group_out /* [col][groups][2] */) {
     const uint32_t NB = 1u << (c - 1);
-    const uint32_t col = blockIdx.x, tid = threadIdx.x;
+    const uint32_t groups = NB / fold;
+    const uint32_t col = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
     const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
     const g1_xyzz* part = partial + (uint64_t)col * partial_stride;
-    const uint32_t G = (NB + RED_THREADS - 1) / RED_THREADS;
-    const uint32_t lo = tid * G;
-    const uint32_t hi = min(lo + G, NB);
+    const uint32_t lo = g * fold;
     g1_xyzz running = xyzz_identity(), acc = xyzz_identity();
-    for (uint32_t b = hi; b-- > lo;) {
+    for (uint32_t b = lo + fold; b-- > lo;) {
         uint32_t e0 = boff[b], e1 = boff[b + 1];
         if (e1 > e0) {
             uint32_t r = rnk[b];
-            for (uint32_t t = e0 / SEG; t <= (e1 - 1) / SEG; t++) xyzz_add(running, xyzz_load(part + r + t));
+            for (uint32_t t = e0 / SEG; t <= (e1 - 1) / SEG; t++) xyzz_add_ni(running, xyzz_load(part + r + t));
         }
-        xyzz_add(acc, running);
+        xyzz_add_ni(acc, running);
     }
-    // bucket b carries weight b+1: sum_b (b+1) B_b = acc + lo * running
-    if (lo < NB && lo) {
-        g1_xyzz t = xyzz_identity();
-        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-            t = xyzz_dbl(t);
-            if ((lo >> bit) & 1) xyzz_add(t, running);
-        }
-        xyzz_add(acc, t);
-    }
-    xyzz_store(&red[tid], acc);
+    g1_xyzz* o = group_out + ((size_t)col * groups + g) * 2;
+    xyzz_store(o, running);
+    xyzz_store(o + 1, acc);
+}
+
+// Reduction, level 2: one CTA per column, one thread per group.
+//   total = sum_g A_g + fold * sum_g g * S_g,   sum_g g * S_g = sum_{g>=1} U_g,  U_g = sum_{h>=g} S_h
+// U is a suffix scan in shared memory (log2(groups) steps), the two sums are tree reductions.
+extern __shared__ uint4 msm_final_smem[];
+__global__ void __launch_bounds__(1024) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
+                                                    g1_affine* out) {
+    g1_xyzz* U = reinterpret_cast<g1_xyzz*>(msm_final_smem);     // [groups]
+    g1_xyzz* A = U + groups;                                      // [groups]
+    const uint32_t col = blockIdx.x, t = threadIdx.x;
+    const g1_xyzz* in = group_in + ((size_t)col * groups + t) * 2;
+    g1_xyzz u = xyzz_load(in);
+    xyzz_store(&U[t], u);
+    xyzz_store(&A[t], xyzz_load(in + 1));
     __syncthreads();
-    for (uint32_t stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
-        if (tid < stride) {
-            g1_xyzz a = xyzz_load(&red[tid]);
-            xyzz_add(a, xyzz_load(&red[tid + stride]));
-            xyzz_store(&red[tid], a);
+    for (uint32_t d = 1; d < groups; d <<= 1) {                   // suffix scan (Hillis-Steele)
+        bool act = t + d < groups;
+        g1_xyzz v;
+        if (act) v = xyzz_load(&U[t + d]);
+        __syncthreads();
+        if (act) { xyzz_add_ni(u, v); xyzz_store(&U[t], u); }
+        __syncthreads();
+    }
+    if (t == 0) xyzz_store(&U[0], xyzz_identity());               // the g = 0 term has weight 0
+    __syncthreads();
+    for (uint32_t stride = groups >> 1; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            g1_xyzz a = xyzz_load(&U[t]);
+            xyzz_add_ni(a, xyzz_load(&U[t + stride]));
+            xyzz_store(&U[t], a);
+            g1_xyzz b = xyzz_load(&A[t]);
+            xyzz_add_ni(b, xyzz_load(&A[t + stride]));
+            xyzz_store(&A[t], b);
         }
         __syncthreads();
     }
-    if (tid == 0) affine_store(out + col, xyzz_to_affine(xyzz_load(&red[0])));
+    if (t == 0) {
+        g1_xyzz w = xyzz_load(&U[0]);
+        for (uint32_t i = 0; i < log_fold; i++) w = xyzz_dbl(w);
+        xyzz_add_ni(w, xyzz_load(&A[0]));
+        affine_store(out + col, xyzz_to_affine(w));
+    }
+}
+
+// ---- test SRS (halo2 `ParamsKZG::setup` shape): g[i] = tau^i G, g_lagrange[i] = l_i(tau) G --------
+__device__ inline g1_affine g1_generator_mul(const fr_t& k_canon) {
+    g1_affine g;
+    g.x = fe_one<FQ>();
+    g.y = add(fe_one<FQ>(), fe_one<FQ>());      // G = (1, 2)
+    g1_xyzz acc = xyzz_identity();
+    bool started = false;
+    for (int i = 7; i >= 0; i--)
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) acc = xyzz_dbl(acc);
+            if ((k_canon.v[i] >> bit) & 1) { xyzz_madd(acc, g, false); started = true; }
+        }
+    return xyzz_to_affine(acc);
+}
+__global__ void k_srs_setup(fr_t tau /*Montgomery*/, uint32_t log_n, g1_affine* g, g1_affine* gl) {
+    const uint32_t n = 1u << log_n;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (g) affine_store(g + i, g1_generator_mul(from_mont(pow_u64(tau, i))));
+    if (gl) {
+        // l_i(tau) = w^i (tau^n - 1) / (n (tau - w^i))
+        fr_t w = fr_t{ZKFHE_FR_ROOT_OF_UNITY_MONT};
+        for (uint32_t s = log_n; s < 28; s++) w = sqr(w);
+        fr_t wi = pow_u64(w, i);
+        fr_t tn = sub(pow_u64(tau, n), fe_one<FR>());
+        fr_t nn = fe_zero<FR>();
+        nn.v[0] = n;
+        fr_t den = mul(to_mont(nn), sub(tau, wi));
+        fr_t li = mul(mul(wi, tn), inv(den));
+        affine_store(gl + i, g1_generator_mul(from_mont(li)));
+    }
+}
+__global__ void k_fr_convert(fr_t* data, uint64_t count, int to_montgomery) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t v = fe_load(data + i);
+    fe_store(data + i, to_montgomery ? to_mont(v) : from_mont(v));
+}
+int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d_g, g1_affine* d_gl) {
+    k_srs_setup<<<((1u << log_n) + 63) / 64, 64, 0, ctx->stream>>>(tau_mont, log_n, d_g, d_gl);
+    ZK_CHECK_LAUNCH(ctx);
+    return ZKFHE_OK;
+}
+int fr_convert(zkfhe_ctx* ctx, fr_t* d, uint64_t count, int to_montgomery) {
+    if (!count) return ZKFHE_OK;
+    k_fr_convert<<<(uint32_t)((count + 255) / 256), 256, 0, ctx->stream>>>(d, count, to_montgomery);
+    ZK_CHECK_LAUNCH(ctx);
+    return ZKFHE_OK;
 }
 
 static uint32_t pick_window(uint32_t log_n) {
@@ -286,6 +366,16 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     ZK_TRY(ws_get(ctx, "msm_soff", (size_t)chunk * (NB + 1) * 4, (void**)&soff));
     ZK_TRY(ws_get(ctx, "msm_sorted", (size_t)chunk * max_refs * 4, (void**)&sorted));
     ZK_TRY(ws_get(ctx, "msm_partial", (size_t)chunk * max_segs * sizeof(g1_xyzz), (void**)&partial));
+    // reduction shape: groups of 2^log_fold buckets, one thread per group in the final CTA
+    uint32_t log_fold = 4;
+    while ((NB >> log_fold) == 0) log_fold--;
+    while ((NB >> log_fold) > 1024) log_fold++;
+    const uint32_t groups = NB >> log_fold;
+    g1_xyzz* grp;
+    ZK_TRY(ws_get(ctx, "msm_groups", (size_t)chunk * groups * 2 * sizeof(g1_xyzz), (void**)&grp));
+    const size_t fsmem = (size_t)groups * 2 * sizeof(g1_xyzz);
+    if (fsmem > 48 * 1024)
+        ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     size_t smem = (size_t)NB * 4;
     if (smem > 48 * 1024)
         ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -300,7 +390,10 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, boff, soff, sorted, max_refs, partial, max_segs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
-        k_msm_reduce<<<nb, RED_THREADS, 0, ctx->stream>>>(c, boff, soff, partial, max_segs, d_out + done);
+        dim3 fgrid((groups + 127) / 128, nb);
+        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, boff, soff, partial, max_segs, grp);
+        ZK_CHECK_LAUNCH(ctx);
+        k_msm_final<<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
         ZK_CHECK_LAUNCH(ctx);
     }
     return ZKFHE_OK;
