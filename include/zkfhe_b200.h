@@ -192,6 +192,20 @@ int zkfhe_chip_constrain_coefficients_in_modulus_field(zkfhe_witness* w, uint32_
 /* PolyChip::safe_trim_leading_zeroes (poly_chip.rs:374-399) */
 int zkfhe_chip_safe_trim_leading_zeroes(zkfhe_witness* w, const zkfhe_assigned_poly* a, uint32_t degree,
                                         zkfhe_assigned_poly* out);
+/* Structure recording (keygen / mock): when switched on before the first chip call, every chip
+ * call also records, per advice cell, a flag byte (1: a gate selector is enabled at this cell,
+ * 2: Constant cell, 4 / 8: assert_is_const(cell, 0 / 1)) and the cell it is copy-constrained to
+ * (0 = none; else ((ctx_id + 1) << 60) | offset), and per lookup cell the advice cell it copies.
+ * This is what halo2-base's builder keeps in `Context::{selector, advice_equality_constraints,
+ * constant_equality_constraints, cells_to_lookup}` when `witness_gen_only` is false. */
+int zkfhe_witness_set_recording(zkfhe_witness* w, int on);
+int zkfhe_witness_download_structure(zkfhe_witness* w, uint32_t ctx_id, uint8_t* h_flags, uint64_t* h_copy);
+int zkfhe_witness_download_lookup_sources(zkfhe_witness* w, uint64_t* h_src);
+int zkfhe_witness_public_cells(const zkfhe_witness* w, uint64_t* h_cell_ids);
+/* The reference's `mock` subcommand (README.md:16-22, halo2 MockProver): checks every gate,
+ * RLC gate, copy / constant constraint and lookup on the device.  Returns ZKFHE_OK or
+ * ZKFHE_ERR_UNSATISFIED; the counts are written either way. */
+int zkfhe_witness_mock(zkfhe_witness* w, uint64_t* n_violations, uint64_t* first_bad_cell);
 /* Sizes so far: advice cells per context, lookup cells, public instances. */
 int zkfhe_witness_counts(const zkfhe_witness* w, uint64_t advice_cells[3], uint64_t* lookup_cells, uint64_t* instances);
 /* Copy a flat vector to the host as Fr (Montgomery): which = 0,1,2 advice of that context,

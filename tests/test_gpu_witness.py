@@ -211,3 +211,94 @@ def test_chip_overflow_guards(ctx):
     with pytest.raises(zk_fhe_b200.ZkfheError) as e:
         a.constrain_mul(a, a)                               # challenge not set yet
     assert e.value.code == -3
+
+
+# ---------------------------------------------------------------- structure / mock -----
+def _cell_index(ctx_sizes):
+    """global index of (ctx, off) in the concatenation of the three contexts"""
+    base = np.concatenate([[0], np.cumsum(ctx_sizes)])
+    return base
+
+
+def _partition_labels(n_total, pairs):
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    if len(pairs):
+        p = np.asarray(pairs, dtype=np.int64)
+        g = coo_matrix((np.ones(len(p), np.int8), (p[:, 0], p[:, 1])), shape=(n_total, n_total))
+    else:
+        g = coo_matrix((n_total, n_total), dtype=np.int8)
+    return connected_components(g, directed=False)[1]
+
+
+def test_recorded_structure_matches_oracle_and_mock_accepts(ctx, bfv_input, oracle_tables, golden_gamma):
+    """Selectors, constant constraints, the copy-constraint partition, lookup wiring and public
+    cells recorded by the kernels == what the oracle's halo2-base restatement records."""
+    from zk_fhe_b200 import bfv
+    circ = bfv.BfvCircuit(ctx, record=True)
+    circ.phase0(bfv_input)
+    circ.phase1(golden_gamma)
+    circ.wit.status()
+    octx = [oracle_tables["phase0"].ctx, oracle_tables["ctx_gate"], oracle_tables["ctx_rlc"]]
+    sizes = [len(c.advice) for c in octx]
+    base = _cell_index(sizes)
+    n_total = int(base[-1])
+    gpu_pairs, gpu_consts = [], set()
+    for cid in range(3):
+        flags, copy = circ.wit.structure(cid)
+        assert np.array_equal((flags & 1).astype(bool), np.array(octx[cid].selector, dtype=bool)), f"selectors ctx {cid}"
+        has = np.nonzero(copy)[0]
+        src_ctx = (copy[has] >> np.uint64(60)).astype(np.int64) - 1
+        src_off = (copy[has] & np.uint64((1 << 60) - 1)).astype(np.int64)
+        gpu_pairs.append(np.stack([base[cid] + has, base[src_ctx] + src_off], axis=1))
+        vals = None
+        for off in np.nonzero(flags & 2)[0]:
+            if vals is None:
+                vals = _canon(circ.wit.download(cid))
+            gpu_consts.add((cid, int(off), vals[off]))
+        gpu_consts |= {(cid, int(o), 0) for o in np.nonzero(flags & 4)[0]}
+        gpu_consts |= {(cid, int(o), 1) for o in np.nonzero(flags & 8)[0]}
+    o_pairs, o_consts = [], set()
+    for c in octx:
+        for (c1, o1), (c2, o2) in c.advice_equality:
+            o_pairs.append((base[c1] + o1, base[c2] + o2))
+        for const, (c1, o1) in c.constant_equality:
+            o_consts.add((c1, o1, const))
+    assert gpu_consts == o_consts
+    la = _partition_labels(n_total, np.concatenate(gpu_pairs))
+    lb = _partition_labels(n_total, o_pairs)
+    # same partition <=> the label pairs form a bijection
+    pairs = np.unique(np.stack([la, lb], axis=1), axis=0)
+    assert len(pairs) == la.max() + 1 == lb.max() + 1
+    # lookup wiring and instances
+    src = circ.wit.lookup_sources()
+    want = [((c.ctx + 1) << 60) | c.offset for c in octx[1].cells_to_lookup]
+    assert [int(x) for x in src] == want
+    pub = circ.wit.public_cells()
+    assert [int(x) for x in pub] == [((c.ctx + 1) << 60) | c.offset for c in oracle_tables["phase0"].make_public]
+    assert circ.wit.mock() == 0
+
+
+def test_mock_rejects_a_wrong_ciphertext_and_a_bad_range(ctx, bfv_input, golden_gamma):
+    import zk_fhe_b200
+    from zk_fhe_b200 import bfv
+    inp = dict(bfv_input)
+    inp["c1"] = list(inp["c1"])
+    inp["c1"][100] = str((int(inp["c1"][100]) + 1) % 536870909)
+    circ = bfv.BfvCircuit(ctx, record=True)
+    circ.phase0(inp).phase1(golden_gamma)
+    with pytest.raises(zk_fhe_b200.ZkfheError) as e:
+        circ.wit.mock()
+    assert e.value.code == -6 and "1 constraint violations" in str(e.value)
+    inp = dict(bfv_input)
+    inp["e0"] = list(inp["e0"])
+    inp["e0"][7] = "20"                                     # outside [0, 19] u [Q-19, Q-1]
+    circ = bfv.BfvCircuit(ctx, record=True)
+    circ.phase0(inp).phase1(golden_gamma)
+    with pytest.raises(zk_fhe_b200.ZkfheError) as e:
+        circ.wit.mock()
+    assert e.value.code == -6
+    w = bfv.BfvCircuit(ctx).wit                             # not recording -> mock is a state error
+    with pytest.raises(zk_fhe_b200.ZkfheError) as e:
+        w.mock()
+    assert e.value.code == -3

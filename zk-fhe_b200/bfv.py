@@ -45,10 +45,10 @@ class BfvCircuit:
     """Two-phase witness generation: `phase0` (bfv.rs:70-165), then -- once the phase-0
     commitment has produced gamma -- `phase1`, the callback (bfv.rs:172-301)."""
 
-    def __init__(self, ctx, params=BfvParams(), lookup_bits=8):
+    def __init__(self, ctx, params=BfvParams(), lookup_bits=8, record=False):
         self.ctx = ctx
         self.params = params
-        self.wit = Witness(ctx, lookup_bits)
+        self.wit = Witness(ctx, lookup_bits, record=record)
         self.P = {}
         self.delta = None
 

@@ -87,6 +87,11 @@ _SIGNATURES = {
     "zkfhe_chip_constrain_from_distribution_chi_key": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64]),
     "zkfhe_chip_constrain_coefficients_in_modulus_field": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint64]),
     "zkfhe_chip_safe_trim_leading_zeroes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p]),
+    "zkfhe_witness_set_recording": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "zkfhe_witness_download_structure": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p, _u8p]),
+    "zkfhe_witness_download_lookup_sources": (_c.c_int, [_c.c_void_p, _u8p]),
+    "zkfhe_witness_public_cells": (_c.c_int, [_c.c_void_p, _u8p]),
+    "zkfhe_witness_mock": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
     "zkfhe_witness_counts": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
     "zkfhe_witness_download": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p]),
     "zkfhe_witness_device_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),

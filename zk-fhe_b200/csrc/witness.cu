@@ -33,11 +33,20 @@ struct DevVec {
     size_t cap = 0, size = 0;
 };
 
+template <class T> struct DevArr {
+    T* p = nullptr;
+    size_t cap = 0;
+};
+
 struct zkfhe_witness {
     zkfhe_ctx* ctx = nullptr;
     uint32_t lookup_bits = 8;
+    bool record = false;            // keygen / mock mode: record selectors, copies, constants
     DevVec adv[3];
     DevVec lk[3];
+    DevArr<uint8_t> flags[3];       // per advice cell (record mode)
+    DevArr<uint64_t> copy[3];
+    DevArr<uint64_t> lk_src[3];     // per lookup cell
     std::vector<zkfhe_cell> make_public;
     fr_t gamma;
     bool have_gamma = false;
@@ -79,6 +88,22 @@ static int vec_reserve(zkfhe_ctx* ctx, DevVec& v, size_t need) {
     }
     v.p = np;
     v.cap = ncap;
+    return ZKFHE_OK;
+}
+
+// metadata arrays follow the capacity of the cell vector they describe
+template <class T> static int arr_reserve(zkfhe_ctx* ctx, DevArr<T>& a, size_t cap, size_t used) {
+    if (cap <= a.cap) return ZKFHE_OK;
+    T* np;
+    ZK_CUDA(ctx, cudaMalloc(&np, cap * sizeof(T)));
+    ZK_CUDA(ctx, cudaMemsetAsync(np, 0, cap * sizeof(T), ctx->stream));
+    if (used && a.p) ZK_CUDA(ctx, cudaMemcpyAsync(np, a.p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (a.p) {
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(ctx, cudaFree(a.p));
+    }
+    a.p = np;
+    a.cap = cap;
     return ZKFHE_OK;
 }
 
@@ -204,100 +229,137 @@ __global__ void k_divide_by_cyclo_finish(uint32_t* status) {
 // ---------------------------------------------------------------------------------------------
 // (1b) chip kernels: one thread per coefficient
 // ---------------------------------------------------------------------------------------------
-struct View {             // an assigned polynomial: coefficient i at p[i * stride]
+struct View {             // an assigned polynomial: coefficient i at p[i * stride], cell id id0 + i * stride
     const fr_t* p;
     uint32_t stride;
+    uint64_t id0;
 };
 struct OutSpan {          // where coefficient i's cells go
     fr_t* adv;            // + i * cpc
     fr_t* lk;             // + i * lpc
     uint32_t cpc, lpc;
+    uint8_t* flags;       // structure recording (null unless the witness records structure)
+    uint64_t* copy;
+    uint64_t* lk_src;
+    uint64_t base_id;     // cell id of adv[0]
 };
+__device__ __forceinline__ Val view_at(const View& a, uint32_t i) {
+    return Val{fe_load(a.p + (size_t)i * a.stride), a.id0 + (uint64_t)i * a.stride};
+}
+__device__ __forceinline__ Emit make_emit(const OutSpan& o, uint32_t i) {
+    Emit e;
+    e.a = o.adv + (size_t)i * o.cpc;
+    e.l = o.lk + (size_t)i * o.lpc;
+    e.na = e.nl = 0;
+    e.flags = o.flags ? o.flags + (size_t)i * o.cpc : nullptr;
+    e.copy = o.flags ? o.copy + (size_t)i * o.cpc : nullptr;
+    e.lk_src = o.flags ? o.lk_src + (size_t)i * o.lpc : nullptr;
+    e.base_id = o.base_id + (uint64_t)i * o.cpc;
+    return e;
+}
 #define CHIP_PROLOGUE                                                   \
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;                 \
     if (i >= len) return;                                               \
-    Emit e{o.adv + (size_t)i * o.cpc, o.lk + (size_t)i * o.lpc, 0, 0};
+    Emit e = make_emit(o, i);
 #define CHIP_EPILOGUE \
     if (e.na != o.cpc || e.nl != o.lpc) atomicOr(status, ST_CELL_COUNT);
 
-__global__ void k_assign_from_poly(const fr_t* canon, fr_t* out, uint32_t len) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    fe_store(out + i, to_mont(fe_load(canon + i)));
+__global__ void k_assign_from_poly(const fr_t* canon, uint32_t len, OutSpan o, uint32_t* status) {
+    CHIP_PROLOGUE
+    e.wit(to_mont(fe_load(canon + i)));
+    CHIP_EPILOGUE
 }
-__global__ void k_assign_constant(fr_t* out, uint64_t v) { fe_store(out, mont_u64(v)); }
+__global__ void k_assign_constant(uint64_t v, OutSpan o) {
+    Emit e = make_emit(o, 0);
+    e.con(mont_u64(v));
+}
 
 __global__ void k_chip_in_range(View a, uint32_t len, uint64_t z, uint64_t y, uint32_t lb, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
     const uint32_t y_bits = 64 - __clzll(y);
-    fr_t c = fe_load(a.p + (size_t)i * a.stride);
+    Val c = view_at(a, i);
     r_check_less_than_safe(e, c, mont_u64(y), y_bits, lb);
-    fr_t in1 = r_is_less_than(e, c, mont_u64(z + 1), y_bits, lb);
-    fr_t nin2 = r_is_less_than(e, c, mont_u64(y - z), y_bits, lb);
-    fr_t in2 = g_not(e, nin2);
+    Val in1 = r_is_less_than(e, c, konst(mont_u64(z + 1)), y_bits, lb);
+    Val nin2 = r_is_less_than(e, c, konst(mont_u64(y - z)), y_bits, lb);
+    Val in2 = g_not(e, nin2);
     g_or(e, in1, in2);
+    e.assert_const_at(1, true);
     CHIP_EPILOGUE
 }
 __global__ void k_chip_chi_key(View a, uint32_t len, uint64_t z, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    fr_t c = fe_load(a.p + (size_t)i * a.stride);
-    fr_t f1 = g_sub(e, c, fe_zero<FR>());
-    fr_t f2 = g_sub(e, c, fe_one<FR>());
-    fr_t f3 = g_sub(e, c, mont_u64(z));
-    fr_t f12 = g_mul(e, f1, f2);
+    Val c = view_at(a, i);
+    Val f1 = g_sub(e, c, konst(fe_zero<FR>()));
+    Val f2 = g_sub(e, c, konst(fe_one<FR>()));
+    Val f3 = g_sub(e, c, konst(mont_u64(z)));
+    Val f12 = g_mul(e, f1, f2);
     g_mul(e, f12, f3);
+    e.assert_const_at(1, false);
     CHIP_EPILOGUE
 }
 __global__ void k_chip_check_lt_safe(View a, uint32_t len, uint64_t b, uint32_t lb, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    fr_t c = fe_load(a.p + (size_t)i * a.stride);
-    r_check_less_than_safe(e, c, mont_u64(b), 64 - __clzll(b), lb);
+    r_check_less_than_safe(e, view_at(a, i), mont_u64(b), 64 - __clzll(b), lb);
     CHIP_EPILOGUE
 }
 __global__ void k_chip_div_mod(View a, uint32_t len, uint64_t q, fr_t bound_mont, uint32_t bound_bits, uint32_t lb,
                                OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    fr_t am = fe_load(a.p + (size_t)i * a.stride);
+    Val am = view_at(a, i);
     fr_t quot;
     uint64_t rem;
-    canon_divmod_u64(from_mont(am), q, quot, rem);
-    fr_t rem_m = mont_u64(rem), div_m = to_mont(quot), q_m = mont_u64(q);
-    e.cell(rem_m); e.cell(q_m); e.cell(div_m); e.cell(am);
-    r_check_less_than_safe(e, div_m, bound_mont, bound_bits, lb);
-    r_check_less_than_safe(e, rem_m, q_m, 64 - __clzll(q), lb);
+    canon_divmod_u64(from_mont(am.v), q, quot, rem);
+    fr_t q_m = mont_u64(q);
+    Val rem_c = e.wit(mont_u64(rem));            // [rem, Q, div, a], gate at 0
+    e.con(q_m);
+    Val div_c = e.wit(to_mont(quot));
+    e.ex(am);
+    e.gate_at(4);
+    r_check_less_than_safe(e, div_c, bound_mont, bound_bits, lb);
+    r_check_less_than_safe(e, rem_c, q_m, 64 - __clzll(q), lb);
     CHIP_EPILOGUE
 }
 __global__ void k_chip_add(View a, View b, uint32_t len, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    g_add(e, fe_load(a.p + (size_t)i * a.stride), fe_load(b.p + (size_t)i * b.stride));
+    g_add(e, view_at(a, i), view_at(b, i));
     CHIP_EPILOGUE
 }
-__global__ void k_chip_scalar_mul(View a, const fr_t* scalar, uint32_t len, OutSpan o, uint32_t* status) {
+__global__ void k_chip_scalar_mul(View a, View scalar, uint32_t len, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    g_mul(e, fe_load(a.p + (size_t)i * a.stride), fe_load(scalar));
+    g_mul(e, view_at(a, i), view_at(scalar, 0));
     CHIP_EPILOGUE
 }
 __global__ void k_chip_is_equal(View a, View b, uint32_t len, OutSpan o, uint32_t* status) {
     CHIP_PROLOGUE
-    g_is_equal(e, fe_load(a.p + (size_t)i * a.stride), fe_load(b.p + (size_t)i * b.stride));
+    g_is_equal(e, view_at(a, i), view_at(b, i));
+    e.assert_const_at(2, true);                  // the bool is cell 6 of is_zero's 8
     CHIP_EPILOGUE
 }
-// constrain_mul's final region [0, a(gamma), b(gamma), c(gamma)]
-__global__ void k_chip_gate4(const fr_t* a, const fr_t* b, const fr_t* c, fr_t* out) {
-    fe_store(out + 0, fe_zero<FR>());
-    fe_store(out + 1, fe_load(a));
-    fe_store(out + 2, fe_load(b));
-    fe_store(out + 3, fe_load(c));
+// constrain_mul's final region [0, a(gamma), b(gamma), c(gamma)], gate at 0
+__global__ void k_chip_gate4(View a, View b, View c, OutSpan o) {
+    Emit e = make_emit(o, 0);
+    e.con(fe_zero<FR>());
+    e.ex(view_at(a, 0));
+    e.ex(view_at(b, 0));
+    e.ex(view_at(c, 0));
+    e.gate_at(4);
+}
+// gate.assert_is_const(cell, 0) on existing cells (safe_trim_leading_zeroes)
+__global__ void k_meta_assert_zero(uint8_t* flags, uint32_t stride, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) flags[(size_t)i * stride] |= META_ASSERT_ZERO;
 }
 
 // RlcChip::compute_rlc_fixed_len: Horner in gamma as a parallel scan of affine maps
-// x -> x * M + V.  One CTA per chain; cells [in0, in1, acc1, in2, acc2, ...].
+// x -> x * M + V.  One CTA per chain; cells [in0, in1, acc1, in2, acc2, ...], RLC gate
+// (a*gamma + b - c on 3 rows) at offsets 0, 2, 4, ...
 static constexpr uint32_t RLC_THREADS = 256;
-__global__ void __launch_bounds__(RLC_THREADS) k_chip_rlc(View in, uint32_t len, fr_t gamma, fr_t* out) {
+__global__ void __launch_bounds__(RLC_THREADS) k_chip_rlc(View in, uint32_t len, fr_t gamma, OutSpan o) {
     __shared__ fr_t M[2][RLC_THREADS], V[2][RLC_THREADS];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (len + RLC_THREADS - 1) / RLC_THREADS;
     const uint32_t lo = min(t * per, len), hi = min(lo + per, len);
+    fr_t* out = o.adv;
     fr_t acc = fe_zero<FR>();
     for (uint32_t j = lo; j < hi; j++) acc = add(mul(acc, gamma), fe_load(in.p + (size_t)j * in.stride));
     fe_store(&M[0][t], pow_u64(gamma, hi - lo));
@@ -321,11 +383,19 @@ __global__ void __launch_bounds__(RLC_THREADS) k_chip_rlc(View in, uint32_t len,
     for (uint32_t j = lo; j < hi; j++) {
         fr_t x = fe_load(in.p + (size_t)j * in.stride);
         acc = add(mul(acc, gamma), x);
+        const uint64_t src = in.id0 + (uint64_t)j * in.stride;
         if (j == 0) {
             fe_store(out, x);
+            if (o.flags) { o.flags[0] = len > 1 ? META_SELECTOR : 0; o.copy[0] = src; }
         } else {
             fe_store(out + 2 * j - 1, x);
             fe_store(out + 2 * j, acc);
+            if (o.flags) {
+                o.flags[2 * j - 1] = 0;
+                o.copy[2 * j - 1] = src;
+                o.flags[2 * j] = j + 1 < len ? META_SELECTOR : 0;
+                o.copy[2 * j] = CELL_NONE;
+            }
         }
     }
 }
@@ -396,13 +466,28 @@ static int chip_out(zkfhe_witness* w, uint32_t ctx_id, uint32_t len, CellCount p
     o->lk = L.p + L.size;
     o->cpc = per.cells;
     o->lpc = per.lookups;
+    o->flags = nullptr;
+    o->copy = nullptr;
+    o->lk_src = nullptr;
+    o->base_id = cell_id(ctx_id, A.size);
+    if (w->record) {
+        ZK_TRY(arr_reserve(ctx, w->flags[ctx_id], A.cap, A.size));
+        ZK_TRY(arr_reserve(ctx, w->copy[ctx_id], A.cap, A.size));
+        ZK_TRY(arr_reserve(ctx, w->lk_src[ctx_id], L.cap ? L.cap : 1, L.size));
+        o->flags = w->flags[ctx_id].p + A.size;
+        o->copy = w->copy[ctx_id].p + A.size;
+        o->lk_src = w->lk_src[ctx_id].p + L.size;
+    }
     *adv_base = A.size;
     A.size += (size_t)len * per.cells;
     L.size += (size_t)len * per.lookups;
     return ZKFHE_OK;
 }
 static inline View view_of(zkfhe_witness* w, const zkfhe_assigned_poly* p) {
-    return View{w->adv[p->ctx_id].p + p->base, p->stride};
+    return View{w->adv[p->ctx_id].p + p->base, p->stride, cell_id(p->ctx_id, p->base)};
+}
+static inline View view_of_cell(zkfhe_witness* w, const zkfhe_cell& c) {
+    return View{w->adv[c.ctx_id].p + c.offset, 1, cell_id(c.ctx_id, c.offset)};
 }
 static int check_poly(zkfhe_witness* w, const zkfhe_assigned_poly* p, const char* what) {
     if (!p) return fail(w->ctx, ZKFHE_ERR_ARG, "%s: null polynomial", what);
@@ -580,8 +665,132 @@ void zkfhe_witness_free(zkfhe_witness* w) {
     for (int i = 0; i < 3; i++) {
         if (w->adv[i].p) cudaFree(w->adv[i].p);
         if (w->lk[i].p) cudaFree(w->lk[i].p);
+        if (w->flags[i].p) cudaFree(w->flags[i].p);
+        if (w->copy[i].p) cudaFree(w->copy[i].p);
+        if (w->lk_src[i].p) cudaFree(w->lk_src[i].p);
     }
     delete w;
+}
+
+int zkfhe_witness_set_recording(zkfhe_witness* w, int on) {
+    if (!w) return ZKFHE_ERR_ARG;
+    for (int i = 0; i < 3; i++)
+        if (w->adv[i].size) return fail(w->ctx, ZKFHE_ERR_STATE, "set_recording: cells were already assigned");
+    w->record = on != 0;
+    return ZKFHE_OK;
+}
+
+int zkfhe_witness_download_structure(zkfhe_witness* w, uint32_t ctx_id, uint8_t* h_flags, uint64_t* h_copy) {
+    if (!w || ctx_id > 2) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = w->ctx;
+    if (!w->record) return fail(ctx, ZKFHE_ERR_STATE, "download_structure: the witness is not recording structure");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = w->adv[ctx_id].size;
+    if (n && h_flags) ZK_CUDA(ctx, cudaMemcpyAsync(h_flags, w->flags[ctx_id].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && h_copy) ZK_CUDA(ctx, cudaMemcpyAsync(h_copy, w->copy[ctx_id].p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_witness_download_lookup_sources(zkfhe_witness* w, uint64_t* h_src) {
+    if (!w || !h_src) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = w->ctx;
+    if (!w->record) return fail(ctx, ZKFHE_ERR_STATE, "download_lookup_sources: the witness is not recording structure");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t off = 0;
+    for (int i = 0; i < 3; i++) {
+        if (w->lk[i].size)
+            ZK_CUDA(ctx, cudaMemcpyAsync(h_src + off, w->lk_src[i].p, w->lk[i].size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        off += w->lk[i].size;
+    }
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_witness_public_cells(const zkfhe_witness* w, uint64_t* h_cell_ids) {
+    if (!w || !h_cell_ids) return ZKFHE_ERR_ARG;
+    for (size_t i = 0; i < w->make_public.size(); i++)
+        h_cell_ids[i] = cell_id(w->make_public[i].ctx_id, w->make_public[i].offset);
+    return ZKFHE_OK;
+}
+
+// ---- mock: check every recorded constraint on the device (the reference's `mock` subcommand) ----
+namespace zkfhe {
+struct MockBases {
+    const fr_t* adv[3];
+};
+__global__ void k_mock_cells(MockBases B, uint32_t ctx_id, uint64_t n, const uint8_t* flags, const uint64_t* copy,
+                             int rlc, fr_t gamma, unsigned long long* out /*[0]=violations, [1]=first bad cell id*/) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr_t* a = B.adv[ctx_id];
+    uint8_t f = flags[i];
+    bool bad = false;
+    if (f & META_SELECTOR) {
+        if (rlc) {
+            if (i + 2 >= n) bad = true;
+            else bad = !eq(add(mul(fe_load(a + i), gamma), fe_load(a + i + 1)), fe_load(a + i + 2));
+        } else {
+            if (i + 3 >= n) bad = true;
+            else bad = !eq(add(fe_load(a + i), mul(fe_load(a + i + 1), fe_load(a + i + 2))), fe_load(a + i + 3));
+        }
+    }
+    fr_t v = fe_load(a + i);
+    if ((f & META_ASSERT_ZERO) && !is_zero(v)) bad = true;
+    if ((f & META_ASSERT_ONE) && !eq(v, fe_one<FR>())) bad = true;
+    uint64_t c = copy[i];
+    if (c != CELL_NONE && !eq(v, fe_load(B.adv[cell_ctx(c)] + cell_off(c)))) bad = true;
+    if (bad) {
+        atomicAdd(out, 1ull);
+        atomicMin(out + 1, (unsigned long long)cell_id(ctx_id, i));
+    }
+}
+__global__ void k_mock_lookups(const fr_t* lk, uint64_t n, uint32_t lookup_bits, unsigned long long* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t c = from_mont(fe_load(lk + i));
+    bool ok = (c.v[1] | c.v[2] | c.v[3] | c.v[4] | c.v[5] | c.v[6] | c.v[7]) == 0 && (c.v[0] >> lookup_bits) == 0;
+    if (!ok) {
+        atomicAdd(out, 1ull);
+        atomicMin(out + 1, (unsigned long long)(0xFull << 60 | i));
+    }
+}
+}  // namespace zkfhe
+
+int zkfhe_witness_mock(zkfhe_witness* w, uint64_t* n_violations, uint64_t* first_bad_cell) {
+    if (!w || !n_violations) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = w->ctx;
+    if (!w->record) return fail(ctx, ZKFHE_ERR_STATE, "mock: the witness is not recording structure");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d_out;
+    ZK_TRY(ws_get(ctx, "mock_out", 16, (void**)&d_out));
+    unsigned long long init[2] = {0, ~0ull};
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_out, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    MockBases B{{w->adv[0].p, w->adv[1].p, w->adv[2].p}};
+    for (uint32_t c = 0; c < 3; c++) {
+        const uint64_t n = w->adv[c].size;
+        if (!n) continue;
+        if (c == 2 && !w->have_gamma) return fail(ctx, ZKFHE_ERR_STATE, "mock: RLC cells without a challenge");
+        k_mock_cells<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(B, c, n, w->flags[c].p, w->copy[c].p, c == 2,
+                                                                        w->gamma, d_out);
+        ZK_CHECK_LAUNCH(ctx);
+        if (w->lk[c].size) {
+            k_mock_lookups<<<(uint32_t)((w->lk[c].size + 255) / 256), 256, 0, ctx->stream>>>(w->lk[c].p, w->lk[c].size,
+                                                                                             w->lookup_bits, d_out);
+            ZK_CHECK_LAUNCH(ctx);
+        }
+    }
+    unsigned long long res[2];
+    ZK_CUDA(ctx, cudaMemcpyAsync(res, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_violations = res[0];
+    if (first_bad_cell) *first_bad_cell = res[1];
+    if (res[0]) {
+        fail(ctx, ZKFHE_ERR_UNSATISFIED, "mock: %llu constraint violations, first at context %u offset %llu", res[0],
+             (unsigned)((res[1] >> 60) - 1), (unsigned long long)(res[1] & ((1ull << 60) - 1)));
+        return ZKFHE_ERR_UNSATISFIED;
+    }
+    return ZKFHE_OK;
 }
 
 int zkfhe_witness_reset(zkfhe_witness* w) {
@@ -594,12 +803,11 @@ int zkfhe_witness_reset(zkfhe_witness* w) {
 
 int zkfhe_chip_from_poly(zkfhe_witness* w, uint32_t ctx_id, const zkfhe_poly* p, zkfhe_assigned_poly* out) {
     W_ENTER(w, ctx_id)
-    (void)status;
     if (!p || !out) return fail(ctx, ZKFHE_ERR_ARG, "from_poly: null pointer");
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_id, p->len, CellCount{1, 0}, &o, &base));
-    k_assign_from_poly<<<blocks_for(p->len), 128, 0, ctx->stream>>>(p->d, o.adv, p->len);
+    k_assign_from_poly<<<blocks_for(p->len), 128, 0, ctx->stream>>>(p->d, p->len, o, status);
     ZK_CHECK_LAUNCH(ctx);
     *out = zkfhe_assigned_poly{ctx_id, 1, base, p->len, 0, p->max_bits};
     return ZKFHE_OK;
@@ -612,7 +820,7 @@ int zkfhe_chip_load_constant(zkfhe_witness* w, uint32_t ctx_id, uint64_t value, 
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_id, 1, CellCount{1, 0}, &o, &base));
-    k_assign_constant<<<1, 1, 0, ctx->stream>>>(o.adv, value);
+    k_assign_constant<<<1, 1, 0, ctx->stream>>>(value, o);
     ZK_CHECK_LAUNCH(ctx);
     *out = zkfhe_cell{ctx_id, 0, base};
     return ZKFHE_OK;
@@ -637,7 +845,7 @@ static int rlc_chain(zkfhe_witness* w, uint32_t ctx_rlc, const zkfhe_assigned_po
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_rlc, 1, CellCount{2 * p->len - 1, 0}, &o, &base));
-    k_chip_rlc<<<1, RLC_THREADS, 0, ctx->stream>>>(view_of(w, p), p->len, w->gamma, o.adv);
+    k_chip_rlc<<<1, RLC_THREADS, 0, ctx->stream>>>(view_of(w, p), p->len, w->gamma, o);
     ZK_CHECK_LAUNCH(ctx);
     *eval = zkfhe_cell{ctx_rlc, 0, base + 2 * (uint64_t)p->len - 2};
     return ZKFHE_OK;
@@ -661,8 +869,7 @@ int zkfhe_chip_constrain_mul(zkfhe_witness* w, uint32_t ctx_gate, uint32_t ctx_r
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_gate, 1, CellCount{4, 0}, &o, &base));
-    const fr_t* R = w->adv[ctx_rlc].p;
-    k_chip_gate4<<<1, 1, 0, ctx->stream>>>(R + ea.offset, R + eb.offset, R + ec.offset, o.adv);
+    k_chip_gate4<<<1, 1, 0, ctx->stream>>>(view_of_cell(w, ea), view_of_cell(w, eb), view_of_cell(w, ec), o);
     ZK_CHECK_LAUNCH(ctx);
     return ZKFHE_OK;
 }
@@ -696,8 +903,7 @@ int zkfhe_chip_scalar_mul(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe_assig
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_gate, a->len, CellCount{4, 0}, &o, &base));
-    k_chip_scalar_mul<<<blocks_for(a->len), 128, 0, ctx->stream>>>(view_of(w, a), w->adv[scalar->ctx_id].p + scalar->offset,
-                                                                  a->len, o, status);
+    k_chip_scalar_mul<<<blocks_for(a->len), 128, 0, ctx->stream>>>(view_of(w, a), view_of_cell(w, *scalar), a->len, o, status);
     ZK_CHECK_LAUNCH(ctx);
     *out = zkfhe_assigned_poly{ctx_gate, 4, base + 3, a->len, 0, mb};
     return ZKFHE_OK;
@@ -797,6 +1003,11 @@ int zkfhe_chip_safe_trim_leading_zeroes(zkfhe_witness* w, const zkfhe_assigned_p
     if (!out) return fail(w->ctx, ZKFHE_ERR_ARG, "safe_trim_leading_zeroes: null output");
     if (degree > a->len - 1) return fail(w->ctx, ZKFHE_ERR_ASSERT, "assertion failed: degree <= self.degree (src/poly_chip.rs:380)");
     const uint32_t drop = a->len - 1 - degree;
+    if (w->record && drop) {     // assert_is_const(coeff, 0) on the trimmed leading coefficients (:382-386)
+        zkfhe_ctx* ctx = w->ctx;
+        k_meta_assert_zero<<<blocks_for(drop), 128, 0, ctx->stream>>>(w->flags[a->ctx_id].p + a->base, a->stride, drop);
+        ZK_CHECK_LAUNCH(ctx);
+    }
     *out = zkfhe_assigned_poly{a->ctx_id, a->stride, a->base + (uint64_t)drop * a->stride, degree + 1, 0, a->max_num_bits};
     return ZKFHE_OK;
 }

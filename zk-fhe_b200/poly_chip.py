@@ -14,11 +14,42 @@ CTX_PHASE0, CTX_GATE, CTX_RLC = 0, 1, 2
 
 
 class Witness:
-    def __init__(self, ctx, lookup_bits=8):
+    def __init__(self, ctx, lookup_bits=8, record=False):
+        """record=True: also record selectors / copy constraints / constants (keygen, mock)."""
         self.ctx = ctx
+        self.lookup_bits = lookup_bits
         h = ctypes.c_void_p()
         ctx._check(ctx.lib.zkfhe_witness_new(ctx.h, lookup_bits, ctypes.byref(h)))
         self.h = h
+        self.record = record
+        if record:
+            ctx._check(ctx.lib.zkfhe_witness_set_recording(h, 1))
+
+    def structure(self, ctx_id):
+        """(flags uint8[n], copy uint64[n]) of one context (recording mode)."""
+        n = self.counts()["advice"][ctx_id]
+        flags = np.zeros(n, dtype=np.uint8)
+        copy = np.zeros(n, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.zkfhe_witness_download_structure(self.h, ctx_id, _addr(flags), _addr(copy)))
+        return flags, copy
+
+    def lookup_sources(self):
+        src = np.zeros(self.counts()["lookups"], dtype=np.uint64)
+        if len(src):
+            self.ctx._check(self.ctx.lib.zkfhe_witness_download_lookup_sources(self.h, _addr(src)))
+        return src
+
+    def public_cells(self):
+        ids = np.zeros(self.counts()["instances"], dtype=np.uint64)
+        if len(ids):
+            self.ctx._check(self.ctx.lib.zkfhe_witness_public_cells(self.h, _addr(ids)))
+        return ids
+
+    def mock(self):
+        """The `mock` subcommand: raises ZkfheError(ZKFHE_ERR_UNSATISFIED) on any violated constraint."""
+        n, first = ctypes.c_uint64(), ctypes.c_uint64()
+        self.ctx._check(self.ctx.lib.zkfhe_witness_mock(self.h, ctypes.byref(n), ctypes.byref(first)))
+        return int(n.value)
 
     def __del__(self):
         try:
