@@ -214,6 +214,43 @@ int zkfhe_witness_download(zkfhe_witness* w, uint32_t which, uint8_t* h_out_fr);
 /* Device address of the same vectors (valid until the next chip call grows the buffer). */
 int zkfhe_witness_device_ptr(zkfhe_witness* w, uint32_t which, uint8_t** d_ptr);
 
+/* ---- keygen ------------------------------------------------------------------------------
+ * `cargo run --example bfv -- ... keygen` (README.md:28-38): from a witness object built in
+ * recording mode on the keygen input (data/bfv/bfv_empty.in) to a proving key resident in HBM:
+ * column counts and break points for 2^k rows (the `configs/<name>.json` pinning), selector /
+ * constant / table columns, the permutation, their commitments (the verifying key).
+ * The SRS for k must be loaded first. */
+typedef struct zkfhe_pk zkfhe_pk;
+int zkfhe_keygen(zkfhe_witness* w, uint32_t k, uint32_t unusable_rows, zkfhe_pk** out);
+void zkfhe_pk_free(zkfhe_pk* pk);
+/* The pinning in the reference's configs/bfv.json schema; `needed` receives the size incl. NUL. */
+int zkfhe_pk_pinning_json(const zkfhe_pk* pk, char* buf, size_t cap, size_t* needed);
+/* out = {k, n_gate0, n_gate1, n_rlc, n_lookup, n_advice, n_perm, n_fixed, n_chunks, usable_rows,
+ *        max_rows, lookup_bits, instances, fx_sigma, fx_const, fx_table} */
+int zkfhe_pk_info(const zkfhe_pk* pk, uint32_t out[16]);
+/* Fixed polynomial `index` as Fr (Montgomery): form 0 = Lagrange values (n), 1 = coefficients (n),
+ * 2 = evaluations on the extended coset zeta * H_ext (4n). */
+int zkfhe_pk_download_fixed(const zkfhe_pk* pk, uint32_t index, uint32_t form, uint8_t* h_out);
+/* The verifying key's commitments: n_fixed G1Affine (Montgomery, 64 bytes each). */
+int zkfhe_pk_fixed_commitments(const zkfhe_pk* pk, uint8_t* h_out);
+
+/* ---- prove -------------------------------------------------------------------------------
+ * `cargo run --example bfv -- ... prove` (README.md:40-46): snark-verifier-sdk `gen_snark_shplonk`
+ * -> halo2 `create_proof`.  The Challenge API makes it two-phase (examples/bfv.rs:92-98): the
+ * phase-0 witness is committed first, the challenge gamma comes back, the caller then runs the
+ * phase-1 chip calls (the reference's callback) and finishes the proof.
+ *   seed32            ChaCha20 key for the blinding factors (the reference uses OS entropy)
+ *   transcript_kind   0 = BLAKE2b (halo2's native transcript; default), 1 = Poseidon (the hash
+ *                     family of the reference's snark-verifier transcript; ~tens of ms on the host)
+ * The proof is a malloc'd byte string (free with zkfhe_proof_free): commitments as canonical
+ * uncompressed points (64 bytes), scalars canonical little-endian (32 bytes), in round order. */
+typedef struct zkfhe_prover zkfhe_prover;
+int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out);
+int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_fr_out);
+int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, size_t* proof_len);
+void zkfhe_prover_free(zkfhe_prover* pr);
+void zkfhe_proof_free(uint8_t* proof);
+
 /* ---- timing hook -------------------------------------------------------------------------
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last
  * NTT / MSM call: the butterfly passes for NTT, the bucket-accumulation kernel for MSM. */

@@ -1,0 +1,130 @@
+"""Fiat-Shamir transcripts (oracle; test-only): independent restatement of the two hashes in
+zk-fhe_b200/csrc/host_ff.h so that the verifier replays exactly what the prover hashed.
+
+  Blake2bTranscript   halo2 `Blake2bWrite`/`Challenge255` shape [UPSTREAM-RECALL]: running
+                      BLAKE2b-512 with one-byte tags; a challenge is the digest of the state so
+                      far reduced from 512 bits (halo2curves `from_uniform_bytes`).
+  PoseidonTranscript  the hash family of snark-verifier's PoseidonTranscript (t=5, rate 4, R_F=8,
+                      R_P=60) with constants from the published Grain-LFSR procedure.  The upstream
+                      crates are un-vendored: equality with their tables is UNPINNED.
+"""
+import hashlib
+
+from .field import R_MOD
+
+TAG = b"zkfhe-b200-transcript-v1"
+
+
+class Blake2bTranscript:
+    def __init__(self):
+        self.h = hashlib.blake2b(digest_size=64)
+        self.h.update(TAG)
+
+    def common_scalar(self, x):
+        self.h.update(b"\x02" + int(x).to_bytes(32, "little"))
+
+    def common_point(self, pt):
+        x, y = (0, 0) if pt is None else pt
+        self.h.update(b"\x01" + x.to_bytes(32, "little") + y.to_bytes(32, "little"))
+
+    def squeeze(self):
+        self.h.update(b"\x00")
+        return int.from_bytes(self.h.copy().digest(), "little") % R_MOD
+
+
+# ---- Poseidon --------------------------------------------------------------------------------
+T, R_F, R_P, N_BITS = 5, 8, 60, 254
+
+
+def _grain_bits():
+    state = []
+    for val, width in ((1, 2), (0, 4), (N_BITS, 12), (T, 12), (R_F, 10), (R_P, 10)):
+        state += [(val >> (width - 1 - i)) & 1 for i in range(width)]
+    state += [1] * 30
+
+    def step():
+        b = state[62] ^ state[51] ^ state[38] ^ state[23] ^ state[13] ^ state[0]
+        state.pop(0)
+        state.append(b)
+        return b
+
+    for _ in range(160):
+        step()
+    while True:
+        b = step()
+        while b == 0:
+            step()
+            b = step()
+        yield step()
+
+
+def poseidon_params():
+    g = _grain_bits()
+
+    def bits(n):
+        v = 0
+        for _ in range(n):
+            v = (v << 1) | next(g)
+        return v
+
+    rc = []
+    while len(rc) < (R_F + R_P) * T:
+        v = bits(N_BITS)
+        if v < R_MOD:
+            rc.append(v)
+    while True:
+        xy = [bits(N_BITS) % R_MOD for _ in range(2 * T)]
+        if len(set(xy)) != 2 * T:
+            continue
+        xs, ys = xy[:T], xy[T:]
+        if any((a + b) % R_MOD == 0 for a in xs for b in ys):
+            continue
+        return rc, [[pow((a + b) % R_MOD, -1, R_MOD) for b in ys] for a in xs]
+
+
+_PARAMS = None
+
+
+def poseidon_permute(s):
+    global _PARAMS
+    if _PARAMS is None:
+        _PARAMS = poseidon_params()
+    rc, mds = _PARAMS
+    half = R_F // 2
+    for r in range(R_F + R_P):
+        s = [(s[i] + rc[r * T + i]) % R_MOD for i in range(T)]
+        if r < half or r >= half + R_P:
+            s = [pow(v, 5, R_MOD) for v in s]
+        else:
+            s[0] = pow(s[0], 5, R_MOD)
+        s = [sum(mds[i][j] * s[j] for j in range(T)) % R_MOD for i in range(T)]
+    return s
+
+
+class PoseidonTranscript:
+    def __init__(self):
+        self.state = [0x7A6B666865] + [0] * (T - 1)
+        self.buf = []
+
+    def common_scalar(self, x):
+        self.buf.append(int(x) % R_MOD)
+
+    def common_point(self, pt):
+        x, y = (0, 0) if pt is None else pt
+        for c in (x, y):
+            self.buf += [c & ((1 << 128) - 1), c >> 128]
+
+    def squeeze(self):
+        self.buf.append(1)
+        while len(self.buf) % 4:
+            self.buf.append(0)
+        for i in range(0, len(self.buf), 4):
+            for j in range(4):
+                self.state[1 + j] = (self.state[1 + j] + self.buf[i + j]) % R_MOD
+            self.state = poseidon_permute(self.state)
+        self.buf = []
+        return self.state[1]
+
+
+def make(kind):
+    return PoseidonTranscript() if kind == 1 else Blake2bTranscript()

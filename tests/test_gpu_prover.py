@@ -1,0 +1,175 @@
+"""keygen / prove on the GPU vs the oracle.
+
+Pinned by reference fixtures: the pinning keygen writes must equal the reference's
+configs/bfv.json (column counts and all 158 break points).  Everything after that
+(commitments, proof) has no reference artefact to compare with -- parity unpinned -- so it
+is checked against definitions (MSM / NTT of the same columns in the oracle) and by the
+oracle's independent verifier accepting the proof and rejecting mutated ones.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bfv as obfv
+from oracle import cbind, curve, field, verifier
+from oracle.poly import Poly as OPoly
+from tests.util import fr_to_mont_array, mont_array_to_fr
+
+pytestmark = pytest.mark.gpu
+TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+
+@pytest.fixture(scope="module")
+def ctx13():
+    import zk_fhe_b200
+    c = zk_fhe_b200.Context(0)
+    c.srs_setup(13, TAU)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def pk13(ctx13, bfv_empty_input):
+    from zk_fhe_b200 import bfv, prover
+    circ = bfv.BfvCircuit(ctx13, record=True)
+    circ.phase0(bfv_empty_input).phase1(7)
+    return prover.keygen(circ.wit, 13, 109)
+
+
+def _vk(pk, unusable_rows):
+    cms = [curve.g1_from_mont_bytes(row.tobytes()) for row in pk.fixed_commitments()]
+    return verifier.Vk(pk.info, unusable_rows, cms)
+
+
+def test_keygen_pinning_equals_reference_bfv_json(pk13, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "bfv_pinning.json")))
+    assert pk13.pinning() == ref
+    info = pk13.info
+    assert (info["n_gate0"], info["n_gate1"], info["n_rlc"], info["n_lookup"]) == (3, 153, 5, 36)
+    assert info["n_advice"] == 197 and info["n_perm"] == 199 and info["n_chunks"] == 100 and info["instances"] == 5121
+
+
+def test_keygen_fixed_columns_match_oracle_layout(pk13, ctx13, bfv_empty_input):
+    tab = obfv.build_tables(bfv_empty_input, 7)
+    info = pk13.info
+    n = 1 << 13
+    # gate selectors of a few columns (first, a middle one, the last) and the RLC selectors
+    sel_cols = tab["gate0"][1] + tab["gate1"][1]
+    for c in (0, 2, 3, 77, 155):
+        want = [1 if q else 0 for q in sel_cols[c]] + [0] * (n - len(sel_cols[c]))
+        assert mont_array_to_fr(pk13.fixed(c)) == want, f"gate selector {c}"
+    for j, s in enumerate(tab["rlc"][1]):
+        want = [1 if q else 0 for q in s] + [0] * (n - len(s))
+        assert mont_array_to_fr(pk13.fixed(156 + j)) == want
+    table = mont_array_to_fr(pk13.fixed(info["fx_table"]))
+    assert table == list(range(256)) + [0] * (n - 256)
+    # sigma columns: a permutation of the positions {delta^c w^r}; unconstrained positions map to themselves
+    w = field.omega(13)
+    seen = set()
+    for c in (0, 5, 100, 196, 197, 198):
+        sig = mont_array_to_fr(pk13.fixed(info["fx_sigma"] + c))
+        assert len(set(sig)) == n and not (seen & set(sig))
+        seen.update(sig)
+        # the last row of every column is never used by the circuit: fixed point of the permutation
+        assert sig[n - 1] == pow(field.FR_DELTA, c, field.R_MOD) * pow(w, n - 1, field.R_MOD) % field.R_MOD
+    # commitment / coefficient / extended forms of one sigma column against the oracle's MSM and NTT
+    _, gl = cbind.srs(13, TAU, want_g=False)
+    col = pk13.fixed(info["fx_sigma"] + 5)
+    assert np.array_equal(pk13.fixed_commitments()[info["fx_sigma"] + 5], cbind.msm(col, gl, n, 1)[0])
+    coef = col.copy()
+    cbind.ntt(coef, 13, 1, inverse=True)
+    assert np.array_equal(pk13.fixed(info["fx_sigma"] + 5, form=1), coef)
+    ext = np.zeros((4 * n, 4), np.uint64)
+    ext[:n] = coef
+    cbind.ntt(ext, 15, 1, coset=True)
+    assert np.array_equal(pk13.fixed(info["fx_sigma"] + 5, form=2), ext)
+
+
+def _prove(ctx, pk, inp, seed, params=None, transcript=0):
+    from zk_fhe_b200 import bfv, prover
+    proof, circ = prover.prove(pk, lambda: bfv.BfvCircuit(ctx, params or bfv.BfvParams()), inp, seed, transcript)
+    inst = mont_array_to_fr(circ.wit.download(4))
+    return proof, inst
+
+
+def test_prove_bfv_in_and_oracle_verifier_accepts(ctx13, pk13, bfv_input):
+    proof, inst = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    assert inst[:1024] == [int(x) for x in bfv_input["pk0"]]
+    vk = _vk(pk13, 109)
+    assert verifier.verify(vk, inst, proof, TAU)
+    # deterministic for a fixed seed, different for another seed (blinding)
+    proof2, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    assert proof2 == proof
+    proof3, _ = _prove(ctx13, pk13, bfv_input, bytes(32))
+    assert proof3 != proof and verifier.verify(vk, inst, proof3, TAU)
+    # soundness smoke: any mutation is rejected
+    rng = random.Random(5)
+    for _ in range(4):
+        bad = bytearray(proof)
+        bad[rng.randrange(len(bad))] ^= 1 << rng.randrange(8)
+        with pytest.raises(verifier.VerifyError):
+            verifier.verify(vk, inst, bytes(bad), TAU)
+    bad_inst = list(inst)
+    bad_inst[2048 + 17] = (bad_inst[2048 + 17] + 1) % 536870909       # a different ciphertext coefficient
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, bad_inst, proof, TAU)
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, inst, proof, TAU + 1)                      # wrong SRS
+
+
+def test_proof_of_a_wrong_ciphertext_is_rejected(ctx13, pk13, bfv_input):
+    import zk_fhe_b200
+    inp = dict(bfv_input)
+    inp["c0"] = list(inp["c0"])
+    inp["c0"][3] = str((int(inp["c0"][3]) + 1) % 536870909)
+    try:
+        proof, inst = _prove(ctx13, pk13, inp, bytes(32))
+    except zk_fhe_b200.ZkfheError as e:
+        assert e.code == -6
+        return
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(_vk(pk13, 109), inst, proof, TAU)
+
+
+def _synthetic_input(rng, N, Q, T, B):
+    pk0 = [rng.randrange(Q) for _ in range(N)]
+    pk1 = [rng.randrange(Q) for _ in range(N)]
+    u = [rng.choice([0, 1, Q - 1]) for _ in range(N)]
+    e0 = [max(-B, min(B, round(rng.gauss(0, 3.2)))) % Q for _ in range(N)]
+    e1 = [max(-B, min(B, round(rng.gauss(0, 3.2)))) % Q for _ in range(N)]
+    m = [rng.randint(-(T // 2), T // 2) % Q for _ in range(N)]
+    cyclo = [1] + [0] * (N - 1) + [1]
+
+    def enc(pk, extra):
+        P = OPoly(pk, Q.bit_length()).mul(OPoly(u, Q.bit_length())).reduce_by_modulus(Q)
+        _, r = P.divide_by_cyclo(OPoly(cyclo, Q.bit_length()), Q)
+        return [(a + b) % Q for a, b in zip(r.coefficients[-N:], extra)]
+    c0 = enc(pk0, [((Q // T) * mi + ei) % Q for mi, ei in zip(m, e0)])
+    c1 = enc(pk1, e1)
+    d = dict(pk0=pk0, pk1=pk1, m=m, u=u, e0=e0, e1=e1, c0=c0, c1=c1, cyclo=cyclo)
+    return {k: [str(x) for x in v] for k, v in d.items()}
+
+
+@pytest.mark.parametrize("transcript", [0, 1])
+def test_small_circuit_end_to_end_both_transcripts(transcript):
+    """N = 16 at k = 10: keygen on zeros, prove a synthetic encryption, verify."""
+    import zk_fhe_b200
+    from zk_fhe_b200 import bfv, prover
+    ctx = zk_fhe_b200.Context(0)
+    k, unusable = 10, 20
+    ctx.srs_setup(k, TAU)
+    params = bfv.BfvParams(N=16, Q=536870909, T=7, B=19)
+    zeros = {key: ["0"] * (17 if key == "cyclo" else 16) for key in bfv.INPUT_KEYS}
+    kg = bfv.BfvCircuit(ctx, params, record=True)
+    kg.phase0(zeros).phase1(3)
+    pk = prover.keygen(kg.wit, k, unusable)
+    inp = _synthetic_input(random.Random(44), 16, params.Q, params.T, params.B)
+    proof, inst = _prove(ctx, pk, inp, bytes(32), params, transcript)
+    vk = _vk(pk, unusable)
+    assert verifier.verify(vk, inst, proof, TAU, transcript_kind=transcript)
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, inst, proof, TAU, transcript_kind=1 - transcript)
+    ctx.close()

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkfhe_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -48,10 +48,17 @@ def build(force=False, verbose=False):
     if (not force and os.path.exists(LIB) and os.path.exists(stamp_path)
             and open(stamp_path).read() == stamp):
         return LIB
-    subprocess.run([sys.executable, os.path.join(CSRC, "gen_ff_ptx.py")], check=True,
-                   stdout=None if verbose else subprocess.DEVNULL)
+    for gen in ("gen_ff_ptx.py", "gen_poseidon.py"):
+        subprocess.run([sys.executable, os.path.join(CSRC, gen)], check=True,
+                       stdout=None if verbose else subprocess.DEVNULL)
     stamp = _stamp()
     nvcc = _nvcc()
+    # headers + flags hash: an object is rebuilt when its source or any header changed
+    hh = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cuh", ".h")):
+                hh.update(open(os.path.join(root, name), "rb").read())
     objs = []
     procs = []
     for src in SOURCES:
@@ -59,18 +66,23 @@ def build(force=False, verbose=False):
         if not os.path.exists(path):
             continue
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        ostamp = hashlib.sha256(hh.digest() + open(path, "rb").read()).hexdigest()
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == ostamp:
+            continue
         cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, p in procs:
+        procs.append((src, obj, ostamp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, obj, ostamp, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             print(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
+        with open(obj + ".stamp", "w") as f:
+            f.write(ostamp)
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.run(cmd, check=True)
     with open(stamp_path, "w") as f:

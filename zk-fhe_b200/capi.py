@@ -92,6 +92,17 @@ _SIGNATURES = {
     "zkfhe_witness_download_lookup_sources": (_c.c_int, [_c.c_void_p, _u8p]),
     "zkfhe_witness_public_cells": (_c.c_int, [_c.c_void_p, _u8p]),
     "zkfhe_witness_mock": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
+    "zkfhe_keygen": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_pk_free": (None, [_c.c_void_p]),
+    "zkfhe_pk_pinning_json": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
+    "zkfhe_pk_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint32)]),
+    "zkfhe_pk_download_fixed": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _u8p]),
+    "zkfhe_pk_fixed_commitments": (_c.c_int, [_c.c_void_p, _u8p]),
+    "zkfhe_prove_begin": (_c.c_int, [_c.c_void_p, _u8p, _c.c_int, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_prove_phase0": (_c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    "zkfhe_prove_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_size_t)]),
+    "zkfhe_prover_free": (None, [_c.c_void_p]),
+    "zkfhe_proof_free": (None, [_c.c_void_p]),
     "zkfhe_witness_counts": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
     "zkfhe_witness_download": (_c.c_int, [_c.c_void_p, _c.c_uint32, _u8p]),
     "zkfhe_witness_device_ptr": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),

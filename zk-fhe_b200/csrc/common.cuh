@@ -127,6 +127,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
             int which, g1_affine* d_out);
 int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d_g, g1_affine* d_gl);
 int fr_convert(zkfhe_ctx* ctx, fr_t* d, uint64_t count, int to_montgomery);
+int points_to_canonical(zkfhe_ctx* ctx, g1_affine* d_pts, uint32_t count);
 int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches);
 
 }  // namespace zkfhe

@@ -313,6 +313,19 @@ int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d
     ZK_CHECK_LAUNCH(ctx);
     return ZKFHE_OK;
 }
+__global__ void k_points_to_canonical(g1_affine* pts, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fe_store(&pts[i].x, from_mont(fe_load(&pts[i].x)));
+    fe_store(&pts[i].y, from_mont(fe_load(&pts[i].y)));
+}
+// In place: Montgomery affine points -> canonical coordinates (proof / transcript encoding).
+int points_to_canonical(zkfhe_ctx* ctx, g1_affine* d_pts, uint32_t count) {
+    if (!count) return ZKFHE_OK;
+    k_points_to_canonical<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_pts, count);
+    ZK_CHECK_LAUNCH(ctx);
+    return ZKFHE_OK;
+}
 int fr_convert(zkfhe_ctx* ctx, fr_t* d, uint64_t count, int to_montgomery) {
     if (!count) return ZKFHE_OK;
     k_fr_convert<<<(uint32_t)((count + 255) / 256), 256, 0, ctx->stream>>>(d, count, to_montgomery);

@@ -1,0 +1,894 @@
+// The `prove` path: a halo2-style PLONKish prover (multi-phase advice, lookup and permutation
+// arguments, quotient on the extended coset, SHPLONK multi-open over KZG) for the BFV circuit,
+// with every step proportional to the domain size on the GPU.
+//
+// It replaces what `gen_snark_shplonk` -> halo2 `create_proof` does on the CPU for the reference
+// [UPSTREAM, un-vendored; SURVEY.md App. C.3 is the recalled spec].  Protocol shape follows halo2
+// (same arguments, same blinding rule, extended coset zeta * H_ext, quotient split in n-sized
+// pieces); the exact message order and byte encoding below are this implementation's own and are
+// what oracle/verifier.py checks -- the reference's proof bytes are not reproducible ("parity
+// unpinned": entropy-seeded RNG, no .snark/.vk ships).
+//
+// Prover polynomial table P (column-major, n rows each), in this order:
+//   advice[n_advice] | A'_l, S'_l (l < n_lookup, interleaved) | Zp_j (j < n_chunks) | Zl_l | R
+// Round structure (W = written to the transcript/proof, C = challenge):
+//   0  vk digest, instances (absorbed)         W phase-0 advice commitments     C gamma_rlc
+//   1  W phase-1 advice commitments            C theta
+//   2  W A'_l, S'_l                            C beta, gamma
+//   3  W Zp_j, Zl_l, R                         C y
+//   4  W h_0, h_1, h_2 (quotient pieces)       C x
+//   5  W evaluations at x * w^rot (order = opening table)
+//   6  SHPLONK: C y', C v, W [h'], C u, W [L/(X-u)]
+#include <cstring>
+#include <new>
+#include "prover.cuh"
+#include "witness.cuh"
+#include "witness_types.cuh"
+
+using namespace zkfhe;
+using host::Fr;
+
+namespace zkfhe {
+
+// rotation sets of the opening argument (exponent of w; ROT_LAST stands for w^usable = w^-(bf+1))
+static constexpr int ROT_LAST = 1000;
+static const int SET_ROTS[6][4] = {{0, 0, 0, 0}, {0, 1, 2, 3}, {0, 1, 2, 0}, {0, -1, 0, 0}, {0, 1, 0, 0}, {0, 1, ROT_LAST, 0}};
+static const int SET_SIZE[6] = {1, 4, 3, 2, 2, 3};
+enum { SET_0 = 0, SET_0123 = 1, SET_012 = 2, SET_0m1 = 3, SET_01 = 4, SET_01L = 5 };
+// distinct points, index into pw tables: x*w^{-1}, x, x*w, x*w^2, x*w^3, x*w^last
+static int point_index(int rot) { return rot == ROT_LAST ? 5 : rot + 1; }
+
+// ---- ChaCha20 (RFC 7539) stream for blinding factors --------------------------------------------
+struct ChaCha20 {
+    uint32_t st[16];
+    uint8_t block[64];
+    int used = 64;
+    static uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+    explicit ChaCha20(const uint8_t key[32]) {
+        static const uint32_t c[4] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+        memcpy(st, c, 16);
+        memcpy(st + 4, key, 32);
+        st[12] = 0; st[13] = 0; st[14] = 0; st[15] = 0;
+    }
+    void next_block() {
+        uint32_t x[16];
+        memcpy(x, st, 64);
+#define ZK_QR(a, b, c, d) x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12); \
+                          x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+        for (int i = 0; i < 10; i++) {
+            ZK_QR(0, 4, 8, 12) ZK_QR(1, 5, 9, 13) ZK_QR(2, 6, 10, 14) ZK_QR(3, 7, 11, 15)
+            ZK_QR(0, 5, 10, 15) ZK_QR(1, 6, 11, 12) ZK_QR(2, 7, 8, 13) ZK_QR(3, 4, 9, 14)
+        }
+#undef ZK_QR
+        for (int i = 0; i < 16; i++) x[i] += st[i];
+        memcpy(block, x, 64);
+        if (++st[12] == 0) ++st[13];
+        used = 0;
+    }
+    void fill(void* out, size_t len) {
+        uint8_t* p = (uint8_t*)out;
+        while (len) {
+            if (used == 64) next_block();
+            size_t take = (size_t)(64 - used) < len ? (size_t)(64 - used) : len;
+            memcpy(p, block + used, take);
+            used += (int)take; p += take; len -= take;
+        }
+    }
+};
+
+// ---- kernels --------------------------------------------------------------------------------------
+struct ColSrc {            // one advice column cut from a flat context
+    const fr_t* base;      // flat cells of the context (or lookup cells)
+    uint64_t start;
+    uint32_t rows;
+};
+// Lagrange columns from flat contexts: rows [0, rows) from the context, rows [usable, n) blinding, else 0
+__global__ void k_fill_columns(fr_t* P, const ColSrc* src, uint32_t n, uint32_t usable, const fr_t* blind /*[ncols][n-usable]*/) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (row >= n) return;
+    const ColSrc s = src[col];
+    fr_t v = fe_zero<FR>();
+    if (row < s.rows) v = fe_load(s.base + s.start + row);
+    else if (row >= usable) v = fe_load(blind + (size_t)col * (n - usable) + (row - usable));
+    fe_store(P + (size_t)col * n + row, v);
+}
+__global__ void k_fill_instance(fr_t* inst, uint32_t n, const fr_t* const* bases, const uint64_t* ids, uint32_t count) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fr_t v = fe_zero<FR>();
+    if (row < count) v = fe_load(bases[cell_ctx(ids[row])] + cell_off(ids[row]));
+    fe_store(inst + row, v);
+}
+// 255-bit random integers -> uniform-ish Fr (Montgomery)
+__global__ void k_random_to_fr(fr_t* d, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t v = fe_load(d + i);
+    v.v[7] &= 0x7fffffffu;
+    fe_store(d + i, to_mont(v));
+}
+
+// Lookup argument, permuted columns (halo2 `permute_expression_pair`): one CTA per lookup column.
+// A' = input sorted ascending; S'[i] = A'[i] at the first row of each run, the other rows take the
+// unused table values in ascending order.  Table = {0..T-1} at rows [0,T), 0 elsewhere.
+extern __shared__ uint32_t lk_smem[];
+__global__ void __launch_bounds__(1024) k_lookup_permute(const fr_t* A_cols, uint64_t a_stride, fr_t* P_out /*A'_0*/,
+                                                         uint64_t out_stride, uint32_t n, uint32_t usable, uint32_t T,
+                                                         const fr_t* blind, uint32_t* status) {
+    uint32_t* hist = lk_smem;            // [T] counts -> start offsets
+    uint32_t* dist = hist + T;           // [T] distinct values before v
+    uint32_t* unus = dist + T;           // [T] unused-value list
+    __shared__ uint32_t s_nunused;
+    const uint32_t l = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const fr_t* A = A_cols + (uint64_t)l * a_stride;
+    fr_t* Ap = P_out + (uint64_t)(2 * l) * out_stride;
+    fr_t* Sp = Ap + out_stride;
+    for (uint32_t v = tid; v < T; v += nt) hist[v] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < usable; i += nt) {
+        fr_t c = from_mont(fe_load(A + i));
+        bool ok = (c.v[1] | c.v[2] | c.v[3] | c.v[4] | c.v[5] | c.v[6] | c.v[7]) == 0 && c.v[0] < T;
+        if (ok) atomicAdd(&hist[c.v[0]], 1u);
+        else atomicOr(status, 1u << 6);          // value not in the table: the witness is unsatisfiable
+    }
+    __syncthreads();
+    if (tid == 0) {                              // T <= 4096: a serial scan is fine here
+        uint32_t run = 0, d = 0, nu = 0;
+        for (uint32_t v = 0; v < T; v++) {
+            uint32_t c = hist[v];
+            hist[v] = run;
+            dist[v] = d;
+            run += c;
+            d += c != 0;
+            if (c == 0 && v >= 1) unus[nu++] = v;
+        }
+        s_nunused = nu;
+    }
+    __syncthreads();
+    // zeros available in the table over the usable rows: rows 0 and [T, usable)
+    const uint32_t first_zero_taken = (T > 1 ? hist[1] : usable) > 0 ? 1u : 0u;   // hist[1] = count of zeros
+    const uint32_t z0 = (usable - T + 1) - first_zero_taken;
+    for (uint32_t p = tid; p < n; p += nt) {
+        fr_t a, s;
+        if (p >= usable) {
+            a = fe_load(blind + (size_t)(2 * l) * (n - usable) + (p - usable));
+            s = fe_load(blind + (size_t)(2 * l + 1) * (n - usable) + (p - usable));
+        } else {
+            uint32_t lo = 0, hi = T;             // largest v with start[v] <= p and a non-empty run
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (hist[mid] <= p) lo = mid; else hi = mid;
+            }
+            const uint32_t v = lo;
+            a = mont_u64(v);
+            if (p == hist[v]) {
+                s = a;
+            } else {
+                uint32_t r = p - dist[v] - 1;    // rank among the repeated rows
+                s = r < z0 ? fe_zero<FR>() : mont_u64(unus[r - z0]);
+            }
+        }
+        fe_store(Ap + p, a);
+        fe_store(Sp + p, s);
+    }
+    (void)s_nunused;
+}
+
+// Grand products.  One CTA per Z column; thread t owns rows [t*per, (t+1)*per) of the usable range.
+//   kind 0 (lookup l):      ratio_i = (A_i + beta)(S_i + gamma) / ((A'_i + beta)(S'_i + gamma))
+//   kind 1 (perm chunk j):  ratio_i = prod_c (v_c,i + beta*delta^c*w^i + gamma) / (v_c,i + beta*sigma_c,i + gamma)
+// Z[0] = 1, Z[i+1] = Z[i] * ratio_i for i < usable; rows (usable, n) are blinding.
+struct GpArgs {
+    fr_t* P;                 // prover polynomial table
+    uint64_t n;
+    uint32_t usable, n_advice, n_lookup, n_chunks, n_perm;
+    uint32_t zp_base, zl_base, ap_base, lookup_adv_base;
+    const fr_t* fixed_lagrange;
+    uint32_t fx_table, fx_const, fx_sigma;
+    const fr_t* inst;
+    const fr_t* delta_pow;
+    const fr_t* tw;          // w^i
+    const fr_t* blind;       // [n_chunks + n_lookup][n - usable - 1] blinding rows of the Z columns
+    fr_t beta, gamma;
+};
+static constexpr uint32_t GP_THREADS = 1024, GP_MAX_PER = 16;
+extern __shared__ uint4 gp_smem[];
+__global__ void __launch_bounds__(GP_THREADS) k_grand_product(const GpArgs g) {
+    fr_t* S = reinterpret_cast<fr_t*>(gp_smem);      // [2][GP_THREADS]
+    const uint32_t z = blockIdx.x;                   // 0..n_chunks-1: permutation chunks, then lookups
+    const bool is_perm = z < g.n_chunks;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (g.usable + GP_THREADS - 1) / GP_THREADS;
+    const uint32_t lo = min(tid * per, g.usable), hi = min(lo + per, g.usable);
+    fr_t* Z = g.P + (uint64_t)(is_perm ? g.zp_base + z : g.zl_base + (z - g.n_chunks)) * g.n;
+    fr_t num[GP_MAX_PER], den[GP_MAX_PER];
+    for (uint32_t i = lo; i < hi; i++) {
+        fr_t nu = fe_one<FR>(), de = fe_one<FR>();
+        if (is_perm) {
+            for (uint32_t c = z * PERM_CHUNK; c < min((z + 1) * PERM_CHUNK, g.n_perm); c++) {
+                const fr_t* col = c < g.n_advice ? g.P + (uint64_t)c * g.n
+                                : c == g.n_advice ? g.fixed_lagrange + (uint64_t)g.fx_const * g.n : g.inst;
+                fr_t v = add(fe_load(col + i), g.gamma);
+                fr_t id = mul(mul(g.beta, fe_load(g.delta_pow + c)), fe_load(g.tw + i));
+                fr_t sg = mul(g.beta, fe_load(g.fixed_lagrange + (uint64_t)(g.fx_sigma + c) * g.n + i));
+                nu = mul(nu, add(v, id));
+                de = mul(de, add(v, sg));
+            }
+        } else {
+            const uint32_t l = z - g.n_chunks;
+            fr_t a = fe_load(g.P + (uint64_t)(g.lookup_adv_base + l) * g.n + i);
+            fr_t s = fe_load(g.fixed_lagrange + (uint64_t)g.fx_table * g.n + i);
+            fr_t ap = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l) * g.n + i);
+            fr_t sp = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l + 1) * g.n + i);
+            nu = mul(add(a, g.beta), add(s, g.gamma));
+            de = mul(add(ap, g.beta), add(sp, g.gamma));
+        }
+        num[i - lo] = nu;
+        den[i - lo] = de;
+    }
+    // batch inversion of this thread's denominators (Montgomery's trick), then local prefix products
+    const uint32_t cnt = hi - lo;
+    fr_t pre[GP_MAX_PER];
+    fr_t acc = fe_one<FR>();
+    for (uint32_t k = 0; k < cnt; k++) { pre[k] = acc; acc = mul(acc, den[k]); }
+    fr_t iacc = inv(acc);
+    for (uint32_t k = cnt; k-- > 0;) {
+        fr_t dinv = mul(iacc, pre[k]);
+        iacc = mul(iacc, den[k]);
+        num[k] = mul(num[k], dinv);              // ratio_k
+    }
+    acc = fe_one<FR>();
+    for (uint32_t k = 0; k < cnt; k++) { acc = mul(acc, num[k]); num[k] = acc; }   // inclusive local products
+    fe_store(&S[tid], acc);
+    __syncthreads();
+    int cur = 0;
+    for (uint32_t d = 1; d < GP_THREADS; d <<= 1) {
+        fr_t v = fe_load(&S[cur * GP_THREADS + tid]);
+        if (tid >= d) v = mul(v, fe_load(&S[cur * GP_THREADS + tid - d]));
+        fe_store(&S[(cur ^ 1) * GP_THREADS + tid], v);
+        cur ^= 1;
+        __syncthreads();
+    }
+    fr_t carry = tid ? fe_load(&S[cur * GP_THREADS + tid - 1]) : fe_one<FR>();
+    if (tid == 0) fe_store(Z, fe_one<FR>());
+    for (uint32_t k = 0; k < cnt; k++) fe_store(Z + lo + k + 1, mul(carry, num[k]));
+    // blinding rows
+    const uint32_t nb = (uint32_t)g.n - g.usable - 1;
+    for (uint32_t r = tid; r < nb; r += GP_THREADS) fe_store(Z + g.usable + 1 + r, fe_load(g.blind + (size_t)z * nb + r));
+}
+// Chain the permutation chunks: Z_j starts where Z_{j-1} ended (row `usable`).
+__global__ void k_perm_chain_carry(const fr_t* P, uint64_t n, uint32_t zp_base, uint32_t n_chunks, uint32_t usable, fr_t* carry) {
+    fr_t acc = fe_one<FR>();
+    for (uint32_t j = 0; j < n_chunks; j++) {
+        fe_store(carry + j, acc);
+        acc = mul(acc, fe_load(P + (uint64_t)(zp_base + j) * n + usable));
+    }
+}
+__global__ void k_perm_chain_scale(fr_t* P, uint64_t n, uint32_t zp_base, uint32_t usable, const fr_t* carry) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (row > usable || j == 0) return;
+    fr_t* z = P + (uint64_t)(zp_base + j) * n + row;
+    fe_store(z, mul(fe_load(z), fe_load(carry + j)));
+}
+
+// ---- quotient ------------------------------------------------------------------------------------------
+struct QArgs {
+    const fr_t* E;           // [C_all][4n] prover polynomials on the extended coset
+    const fr_t* F;           // [n_fixed][4n]
+    const fr_t* inst_ext;    // [4n]
+    const fr_t* tw_ext;      // w_ext^j
+    const fr_t* ypow;        // y^t, t < NE
+    const fr_t* delta_pow;
+    fr_t* part;              // [groups][4n] partial sums
+    uint32_t n4, rot;        // 4n, extended-index step of one base-domain rotation (= 4)
+    uint32_t n_gate, n_rlc, rlc_base, n_advice, n_lookup, n_chunks, n_perm, NE;
+    uint32_t zp_base, zl_base, ap_base, lookup_adv_base, usable;
+    uint32_t fx_qgate, fx_qrlc, fx_const, fx_table, fx_l0, fx_sigma;
+    uint32_t cols_per_group;
+    fr_t gamma_rlc, beta, gamma, zeta;
+};
+#define QE(col, r) fe_load(q.E + (uint64_t)(col) * q.n4 + (((r) + row) & (q.n4 - 1)))
+#define QF(col) fe_load(q.F + (uint64_t)(col) * q.n4 + row)
+
+__global__ void k_quotient_gates(const QArgs q) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, grp = blockIdx.y;
+    if (row >= q.n4) return;
+    fr_t acc = fe_zero<FR>();
+    const uint32_t c0 = grp * q.cols_per_group, c1 = min(c0 + q.cols_per_group, q.n_gate + q.n_rlc);
+    for (uint32_t c = c0; c < c1; c++) {
+        fr_t e;
+        if (c < q.n_gate) {
+            fr_t a0 = QE(c, 0), a1 = QE(c, q.rot), a2 = QE(c, 2 * q.rot), a3 = QE(c, 3 * q.rot);
+            e = mul(QF(q.fx_qgate + c), sub(add(a0, mul(a1, a2)), a3));
+        } else {
+            const uint32_t r = c - q.n_gate, col = q.rlc_base + r;
+            fr_t a0 = QE(col, 0), a1 = QE(col, q.rot), a2 = QE(col, 2 * q.rot);
+            e = mul(QF(q.fx_qrlc + r), sub(add(mul(a0, q.gamma_rlc), a1), a2));
+        }
+        acc = add(acc, mul(e, fe_load(q.ypow + (q.NE - 1 - c))));
+    }
+    fe_store(q.part + (uint64_t)grp * q.n4 + row, acc);
+}
+
+__device__ __forceinline__ fr_t perm_col_ext(const QArgs& q, uint32_t c, uint32_t row) {
+    return c < q.n_advice ? QE(c, 0) : c == q.n_advice ? QF(q.fx_const) : fe_load(q.inst_ext + row);
+}
+// expression indices: Bp+0: l0(1-Z0); Bp+1: l_last(Zm^2-Zm); Bp+1+j (j=1..m-1): l0(Z_j - Z_{j-1}(w^last X));
+// Bp+1+m+j: l_active(Z_j(wX) prod(v+beta*sigma+gamma) - Z_j(X) prod(v+beta*delta^c*X+gamma))
+__global__ void k_quotient_perm(const QArgs q, uint32_t part_base) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (row >= q.n4) return;
+    const uint32_t Bp = q.n_gate + q.n_rlc, m = q.n_chunks;
+    const fr_t one = fe_one<FR>();
+    const fr_t l0 = QF(q.fx_l0), l_last = QF(q.fx_l0 + 1), l_act = QF(q.fx_l0 + 2);
+    const fr_t zj = QE(q.zp_base + j, 0), zj_w = QE(q.zp_base + j, q.rot);
+    fr_t acc = fe_zero<FR>();
+    if (j == 0) acc = add(acc, mul(mul(l0, sub(one, zj)), fe_load(q.ypow + (q.NE - 1 - Bp))));
+    if (j == m - 1) acc = add(acc, mul(mul(l_last, sub(sqr(zj), zj)), fe_load(q.ypow + (q.NE - 1 - (Bp + 1)))));
+    if (j >= 1) {
+        fr_t prev = QE(q.zp_base + j - 1, q.usable * q.rot);
+        acc = add(acc, mul(mul(l0, sub(zj, prev)), fe_load(q.ypow + (q.NE - 1 - (Bp + 1 + j)))));
+    }
+    fr_t x = mul(q.zeta, fe_load(q.tw_ext + row));
+    fr_t left = zj_w, right = zj;
+    for (uint32_t c = j * PERM_CHUNK; c < min((j + 1) * PERM_CHUNK, q.n_perm); c++) {
+        fr_t v = add(perm_col_ext(q, c, row), q.gamma);
+        left = mul(left, add(v, mul(q.beta, QF(q.fx_sigma + c))));
+        right = mul(right, add(v, mul(mul(q.beta, fe_load(q.delta_pow + c)), x)));
+    }
+    acc = add(acc, mul(mul(l_act, sub(left, right)), fe_load(q.ypow + (q.NE - 1 - (Bp + 1 + m + j)))));
+    fe_store(q.part + (uint64_t)(part_base + j) * q.n4 + row, acc);
+}
+// per lookup l, expressions Bl+5l+{0..4}:
+//  l0(1-Z); l_last(Z^2-Z); l_active(Z(wX)(A'+beta)(S'+gamma) - Z(A+beta)(S+gamma)); l0(A'-S'); l_active(A'-S')(A'-A'(w^-1 X))
+__global__ void k_quotient_lookup(const QArgs q, uint32_t part_base) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+    if (row >= q.n4) return;
+    const uint32_t Bl = q.n_gate + q.n_rlc + 2 * q.n_chunks + 1 + 5 * l;
+    const fr_t one = fe_one<FR>();
+    const fr_t l0 = QF(q.fx_l0), l_last = QF(q.fx_l0 + 1), l_act = QF(q.fx_l0 + 2);
+    const fr_t z = QE(q.zl_base + l, 0), z_w = QE(q.zl_base + l, q.rot);
+    const fr_t a = QE(q.lookup_adv_base + l, 0), s = QF(q.fx_table);
+    const fr_t ap = QE(q.ap_base + 2 * l, 0), ap_m1 = QE(q.ap_base + 2 * l, q.n4 - q.rot), sp = QE(q.ap_base + 2 * l + 1, 0);
+    fr_t acc = mul(mul(l0, sub(one, z)), fe_load(q.ypow + (q.NE - 1 - Bl)));
+    acc = add(acc, mul(mul(l_last, sub(sqr(z), z)), fe_load(q.ypow + (q.NE - 2 - Bl))));
+    fr_t left = mul(z_w, mul(add(ap, q.beta), add(sp, q.gamma)));
+    fr_t right = mul(z, mul(add(a, q.beta), add(s, q.gamma)));
+    acc = add(acc, mul(mul(l_act, sub(left, right)), fe_load(q.ypow + (q.NE - 3 - Bl))));
+    fr_t d = sub(ap, sp);
+    acc = add(acc, mul(mul(l0, d), fe_load(q.ypow + (q.NE - 4 - Bl))));
+    acc = add(acc, mul(mul(l_act, mul(d, sub(ap, ap_m1))), fe_load(q.ypow + (q.NE - 5 - Bl))));
+    fe_store(q.part + (uint64_t)(part_base + l) * q.n4 + row, acc);
+}
+// h_ext[row] = (sum_g part[g][row]) / (X^n - 1); X^n - 1 takes 4 values on the extended coset
+__global__ void k_quotient_finish(const fr_t* part, uint32_t groups, uint32_t n4, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n4) return;
+    fr_t acc = fe_zero<FR>();
+    for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * n4 + row));
+    const uint32_t r = row & 3;
+    fe_store(h_ext + row, mul(acc, r == 0 ? zh0 : r == 1 ? zh1 : r == 2 ? zh2 : zh3));
+}
+
+// ---- evaluations and linear combinations ----------------------------------------------------------
+__global__ void k_powers(fr_t* out, fr_t base, uint32_t n) {   // out[i] = base^i
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fe_store(out + i, pow_u64(base, i));
+}
+struct EvalTask {
+    const fr_t* poly;    // n coefficients
+    uint32_t point;      // index into the power tables
+};
+__global__ void __launch_bounds__(256) k_eval(const EvalTask* tasks, const fr_t* pw /*[6][n]*/, uint32_t n, fr_t* out) {
+    __shared__ fr_t red[256];
+    const EvalTask t = tasks[blockIdx.x];
+    const fr_t* p = pw + (uint64_t)t.point * n;
+    fr_t acc = fe_zero<FR>();
+    for (uint32_t i = threadIdx.x; i < n; i += 256) acc = add(acc, mul(fe_load(t.poly + i), fe_load(p + i)));
+    fe_store(&red[threadIdx.x], acc);
+    __syncthreads();
+    for (uint32_t s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) fe_store(&red[threadIdx.x], add(fe_load(&red[threadIdx.x]), fe_load(&red[threadIdx.x + s])));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fe_store(out + blockIdx.x, fe_load(&red[0]));
+}
+// out[row] = sum_j coef[j] * polys[j][row]
+__global__ void k_lincomb(const fr_t* const* polys, const fr_t* coef, uint32_t m, uint32_t n, fr_t* out) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fr_t acc = fe_zero<FR>();
+    for (uint32_t j = 0; j < m; j++) acc = add(acc, mul(fe_load(coef + j), fe_load(polys[j] + row)));
+    fe_store(out + row, acc);
+}
+// SHPLONK quotient on the coset zeta*H: acc[row] += scale * (f[row] - r(c)) / Z(c), c = zeta * w^row.
+// r and Z are given by their coefficients (degree <= 3 and <= 4).
+struct SmallPoly { fr_t c[5]; uint32_t len; };
+__device__ __forceinline__ fr_t small_eval(const SmallPoly& p, const fr_t& x) {
+    fr_t acc = fe_zero<FR>();
+    for (int i = (int)p.len - 1; i >= 0; i--) acc = add(mul(acc, x), p.c[i]);
+    return acc;
+}
+__global__ void k_shplonk_accumulate(const fr_t* f_coset, SmallPoly r, SmallPoly z, fr_t scale, fr_t zeta, const fr_t* tw,
+                                     uint32_t n, fr_t* acc, int first) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fr_t x = mul(zeta, fe_load(tw + row));
+    fr_t v = mul(mul(sub(fe_load(f_coset + row), small_eval(r, x)), inv(small_eval(z, x))), scale);
+    fe_store(acc + row, first ? v : add(fe_load(acc + row), v));
+}
+// h_comb = sum_i x^(n*i) h_i
+__global__ void k_axpy3(const fr_t* h, uint32_t n, fr_t s1, fr_t s2, fr_t* out) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fe_store(out + row, add(fe_load(h + row), add(mul(s1, fe_load(h + n + row)), mul(s2, fe_load(h + 2 * (uint64_t)n + row)))));
+}
+__global__ void k_sub_const0(fr_t* p, fr_t c) { fe_store(p, sub(fe_load(p), c)); }
+
+}  // namespace zkfhe
+
+// =============================================================================================================
+struct zkfhe_prover {
+    zkfhe_pk* pk = nullptr;
+    zkfhe_ctx* ctx = nullptr;
+    host::Transcript tr;
+    ChaCha20 rng;
+    int stage = 0;
+    uint32_t C_all = 0, ap_base = 0, zp_base = 0, zl_base = 0, r_col = 0, lookup_adv_base = 0;
+    fr_t *P = nullptr, *E = nullptr, *inst = nullptr, *inst_ext = nullptr, *blind = nullptr, *misc = nullptr;
+    Fr gamma_rlc, theta, beta, gamma, y, x;
+    float ms_commit = 0, ms_ntt = 0, ms_quotient = 0, ms_open = 0;
+    zkfhe_prover(const uint8_t seed[32], int kind) : tr(kind), rng(seed) {}
+};
+
+namespace zkfhe {
+
+static inline fr_t dev(const Fr& a) { fr_t r; memcpy(r.v, a.l, 32); return r; }
+
+// commit `count` Lagrange-basis (basis 1) or coefficient-basis (basis 0) columns and write the points
+static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count, int basis) {
+    zkfhe_ctx* ctx = pr->ctx;
+    g1_affine* d_pts;
+    ZK_TRY(ws_get(ctx, "pr_points", (size_t)count * sizeof(g1_affine), (void**)&d_pts));
+    ZK_TRY(msm_run(ctx, d_cols, pr->pk->n, pr->pk->k, count, basis, d_pts));
+    ZK_TRY(points_to_canonical(ctx, d_pts, count));
+    std::vector<std::array<uint64_t, 8>> h(count);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pts, (size_t)count * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& p : h) pr->tr.write_point(p.data(), p.data() + 4);
+    return ZKFHE_OK;
+}
+
+// fresh blinding factors: `count` Fr elements (Montgomery) at pr->blind + offset
+static int fill_random(zkfhe_prover* pr, size_t offset, uint32_t count) {
+    zkfhe_ctx* ctx = pr->ctx;
+    std::vector<uint8_t> h((size_t)count * 32);
+    pr->rng.fill(h.data(), h.size());
+    ZK_CUDA(ctx, cudaMemcpyAsync(pr->blind + offset, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_random_to_fr<<<(count + 255) / 256, 256, 0, ctx->stream>>>(pr->blind + offset, count);
+    ZK_CHECK_LAUNCH(ctx);
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // `h` is about to go out of scope
+    return ZKFHE_OK;
+}
+
+static int fill_advice(zkfhe_prover* pr, zkfhe_witness* w, uint32_t first_col, const std::vector<ColSrc>& src) {
+    zkfhe_ctx* ctx = pr->ctx;
+    const zkfhe_pk* pk = pr->pk;
+    const uint32_t nb = pk->n - pk->usable, count = (uint32_t)src.size();
+    ColSrc* d_src;
+    ZK_TRY(ws_get(ctx, "pr_colsrc", src.size() * sizeof(ColSrc), (void**)&d_src));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_src, src.data(), src.size() * sizeof(ColSrc), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(fill_random(pr, 0, count * nb));
+    dim3 grid((pk->n + 255) / 256, count);
+    k_fill_columns<<<grid, 256, 0, ctx->stream>>>(pr->P + (size_t)first_col * pk->n, d_src, pk->n, pk->usable, pr->blind);
+    ZK_CHECK_LAUNCH(ctx);
+    (void)w;
+    return ZKFHE_OK;
+}
+
+}  // namespace zkfhe
+
+extern "C" {
+
+void zkfhe_prover_free(zkfhe_prover* pr) {
+    if (!pr) return;
+    cudaSetDevice(pr->ctx->device);
+    cudaStreamSynchronize(pr->ctx->stream);
+    fr_t* bufs[] = {pr->P, pr->E, pr->inst, pr->inst_ext, pr->blind, pr->misc};
+    for (auto b : bufs) if (b) cudaFree(b);
+    delete pr;
+}
+
+void zkfhe_proof_free(uint8_t* proof) { free(proof); }
+
+int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out) {
+    if (!pk || !seed32 || !out) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = pk->ctx;
+    if (transcript_kind != host::TRANSCRIPT_BLAKE2B && transcript_kind != host::TRANSCRIPT_POSEIDON)
+        return fail(ctx, ZKFHE_ERR_ARG, "prove_begin: unknown transcript kind %d", transcript_kind);
+    if (ctx->srs_k != pk->k) return fail(ctx, ZKFHE_ERR_STATE, "prove_begin: SRS for k=%u is not loaded", pk->k);
+    if (pk->lookup_bits > 12) return fail(ctx, ZKFHE_ERR_ARG, "prove: lookup_bits > 12 is not supported by the lookup kernels");
+    if ((pk->usable + GP_THREADS - 1) / GP_THREADS > GP_MAX_PER) return fail(ctx, ZKFHE_ERR_ARG, "prove: k too large for the grand-product kernel");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    zkfhe_prover* pr = new (std::nothrow) zkfhe_prover(seed32, transcript_kind);
+    if (!pr) return fail(ctx, ZKFHE_ERR_CUDA, "out of host memory");
+    pr->pk = pk;
+    pr->ctx = ctx;
+    pr->lookup_adv_base = pk->n_gate0 + pk->n_gate1 + pk->n_rlc;
+    pr->ap_base = pk->n_advice;
+    pr->zp_base = pr->ap_base + 2 * pk->n_lookup;
+    pr->zl_base = pr->zp_base + pk->n_chunks;
+    pr->r_col = pr->zl_base + pk->n_lookup;
+    pr->C_all = pr->r_col + 1;
+    const size_t n = pk->n;
+    cudaError_t e = cudaMalloc(&pr->P, (size_t)pr->C_all * n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->E, ((size_t)pr->C_all * n * 32) << EXT_SHIFT);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->inst, n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->inst_ext, (n * 32) << EXT_SHIFT);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->blind, ((size_t)pr->C_all * (n - pk->usable) + n) * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->misc, (size_t)16 * (n << EXT_SHIFT) * 32);
+    if (e != cudaSuccess) {
+        zkfhe_prover_free(pr);
+        return fail(ctx, ZKFHE_ERR_CUDA, "prove_begin: cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    *out = pr;
+    return ZKFHE_OK;
+}
+
+// Round 0: absorb vk digest + instances, commit the phase-0 advice columns, return gamma (Fr, Montgomery).
+int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out) {
+    if (!pr || !w || !h_gamma_out) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = pr->ctx;
+    zkfhe_pk* pk = pr->pk;
+    if (pr->stage != 0) return fail(ctx, ZKFHE_ERR_STATE, "prove_phase0: called out of order");
+    if (w->adv[0].size != pk->cells[0] || w->make_public.size() != pk->instances)
+        return fail(ctx, ZKFHE_ERR_ARG, "prove_phase0: witness shape differs from the proving key (%zu cells, key has %llu)",
+                    w->adv[0].size, (unsigned long long)pk->cells[0]);
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = pk->n;
+    // instance column
+    const fr_t* bases[3] = {w->adv[0].p, w->adv[1].p, w->adv[2].p};
+    uint8_t* d_tmp;
+    const size_t ids_bytes = pk->public_cells.size() * 8;
+    ZK_TRY(ws_get(ctx, "pr_inst_ids", 64 + ids_bytes + 8, (void**)&d_tmp));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_tmp, bases, sizeof bases, cudaMemcpyHostToDevice, ctx->stream));
+    if (ids_bytes) ZK_CUDA(ctx, cudaMemcpyAsync(d_tmp + 64, pk->public_cells.data(), ids_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_instance<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pr->inst, n, (const fr_t* const*)d_tmp, (const uint64_t*)(d_tmp + 64),
+                                                             (uint32_t)pk->instances);
+    ZK_CHECK_LAUNCH(ctx);
+    std::vector<Fr> h_inst(pk->instances);
+    if (pk->instances)
+        ZK_CUDA(ctx, cudaMemcpyAsync(h_inst.data(), pr->inst, pk->instances * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pr->tr.common_scalar(pk->vk_digest);
+    for (auto& v : h_inst) pr->tr.common_scalar(v);
+    // phase-0 advice columns
+    std::vector<ColSrc> src;
+    for (uint32_t j = 0; j < pk->n_gate0; j++) src.push_back(ColSrc{w->adv[0].p, pk->cut[0].start[j], pk->cut[0].rows[j]});
+    ZK_TRY(fill_advice(pr, w, 0, src));
+    ZK_TRY(commit_and_write(pr, pr->P, pk->n_gate0, 1));
+    pr->gamma_rlc = pr->tr.squeeze();
+    memcpy(h_gamma_out, pr->gamma_rlc.l, 32);
+    pr->stage = 1;
+    return ZKFHE_OK;
+}
+
+int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, size_t* proof_len) {
+    if (!pr || !w || !proof_out || !proof_len) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = pr->ctx;
+    zkfhe_pk* pk = pr->pk;
+    if (pr->stage != 1) return fail(ctx, ZKFHE_ERR_STATE, "prove_finish: zkfhe_prove_phase0 must run first");
+    size_t lookups = 0;
+    for (int c = 0; c < 3; c++) lookups += w->lk[c].size;
+    if (w->adv[1].size != pk->cells[1] || w->adv[2].size != pk->cells[2] || lookups != pk->lookups || w->lk[1].size != lookups)
+        return fail(ctx, ZKFHE_ERR_ARG, "prove_finish: witness shape differs from the proving key");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t* status;
+    {
+        void* p;
+        const bool fresh = ctx->ws.find("status") == ctx->ws.end();
+        ZK_TRY(ws_get(ctx, "status", 256, &p));
+        if (fresh) ZK_CUDA(ctx, cudaMemsetAsync(p, 0, 256, ctx->stream));
+        status = (uint32_t*)p;
+    }
+    const uint32_t n = pk->n, k = pk->k, usable = pk->usable, nb = n - usable;
+    const uint32_t n4 = n << EXT_SHIFT, k4 = k + EXT_SHIFT;
+    const uint32_t n_gate = pk->n_gate0 + pk->n_gate1;
+    NttDomain *dom, *dom4;
+    ZK_TRY(ntt_domain(ctx, k, &dom));
+    ZK_TRY(ntt_domain(ctx, k4, &dom4));
+
+    // ---- round 1: phase-1 advice -----------------------------------------------------------------
+    {
+        std::vector<ColSrc> src;
+        for (uint32_t j = 0; j < pk->n_gate1; j++) src.push_back(ColSrc{w->adv[1].p, pk->cut[1].start[j], pk->cut[1].rows[j]});
+        for (uint32_t j = 0; j < pk->n_rlc; j++) src.push_back(ColSrc{w->adv[2].p, pk->cut[2].start[j], pk->cut[2].rows[j]});
+        for (uint32_t j = 0; j < pk->n_lookup; j++) {
+            uint64_t start = (uint64_t)j * pk->max_rows;
+            uint32_t rows = (uint32_t)(lookups - start < pk->max_rows ? lookups - start : pk->max_rows);
+            src.push_back(ColSrc{w->lk[1].p, start, rows});
+        }
+        ZK_TRY(fill_advice(pr, w, pk->n_gate0, src));
+        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pk->n_gate0 * n, pk->n_advice - pk->n_gate0, 1));
+    }
+    pr->theta = pr->tr.squeeze();
+
+    // ---- round 2: lookup permuted columns -----------------------------------------------------------
+    {
+        ZK_TRY(fill_random(pr, 0, 2 * pk->n_lookup * nb));
+        const uint32_t T = 1u << pk->lookup_bits;
+        k_lookup_permute<<<pk->n_lookup, 1024, 3 * T * 4, ctx->stream>>>(
+            pr->P + (size_t)pr->lookup_adv_base * n, n, pr->P + (size_t)pr->ap_base * n, n, n, usable, T, pr->blind, status);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->ap_base * n, 2 * pk->n_lookup, 1));
+        uint32_t st = 0;
+        ZK_CUDA(ctx, cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (st & (1u << 6)) {
+            ZK_CUDA(ctx, cudaMemsetAsync(status, 0, 4, ctx->stream));
+            return fail(ctx, ZKFHE_ERR_UNSATISFIED, "prove: a lookup cell is outside the table [0, 2^%u)", pk->lookup_bits);
+        }
+    }
+    pr->beta = pr->tr.squeeze();
+    pr->gamma = pr->tr.squeeze();
+
+    // ---- round 3: grand products + random polynomial ---------------------------------------------------
+    {
+        const uint32_t nz = pk->n_chunks + pk->n_lookup;
+        ZK_TRY(fill_random(pr, 0, nz * (nb - 1) + n));
+        GpArgs g{};
+        g.P = pr->P; g.n = n; g.usable = usable; g.n_advice = pk->n_advice; g.n_lookup = pk->n_lookup;
+        g.n_chunks = pk->n_chunks; g.n_perm = pk->n_perm; g.zp_base = pr->zp_base; g.zl_base = pr->zl_base;
+        g.ap_base = pr->ap_base; g.lookup_adv_base = pr->lookup_adv_base; g.fixed_lagrange = pk->fixed_lagrange;
+        g.fx_table = pk->fx_table; g.fx_const = pk->fx_const; g.fx_sigma = pk->fx_sigma; g.inst = pr->inst;
+        g.delta_pow = pk->delta_pow; g.tw = dom->tw_fwd; g.blind = pr->blind; g.beta = dev(pr->beta); g.gamma = dev(pr->gamma);
+        const size_t smem = 2 * GP_THREADS * sizeof(fr_t);
+        ZK_CUDA(ctx, cudaFuncSetAttribute(k_grand_product, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_grand_product<<<nz, GP_THREADS, smem, ctx->stream>>>(g);
+        ZK_CHECK_LAUNCH(ctx);
+        fr_t* carry = pr->misc;
+        k_perm_chain_carry<<<1, 1, 0, ctx->stream>>>(pr->P, n, pr->zp_base, pk->n_chunks, usable, carry);
+        ZK_CHECK_LAUNCH(ctx);
+        dim3 grid((usable + 256) / 256, pk->n_chunks);
+        k_perm_chain_scale<<<grid, 256, 0, ctx->stream>>>(pr->P, n, pr->zp_base, usable, carry);
+        ZK_CHECK_LAUNCH(ctx);
+        // random polynomial R: n random values (its Lagrange form is as random as any)
+        ZK_CUDA(ctx, cudaMemcpyAsync(pr->P + (size_t)pr->r_col * n, pr->blind + (size_t)nz * (nb - 1), (size_t)n * 32,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->zp_base * n, nz + 1, 1));
+    }
+    pr->y = pr->tr.squeeze();
+
+    // ---- round 4: quotient -----------------------------------------------------------------------------
+    fr_t* h_ext = pr->misc;                       // [4n]
+    fr_t* h_coef = pr->misc + n4;                 // [4n] -> pieces h_0..h_2 in the first 3n
+    {
+        // coefficient form of everything (Lagrange values are no longer needed), then the extended coset
+        ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->P, n, k, pr->C_all, 1, 0));
+        ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst, n, k, 1, 1, 0));
+        ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->E, n4, k4, pr->C_all, 0, 1));
+        ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst_ext, n4, k4, 1, 0, 1));
+        const uint32_t NE = n_gate + pk->n_rlc + 2 * pk->n_chunks + 1 + 5 * pk->n_lookup;
+        std::vector<Fr> ypow(NE);
+        ypow[0] = host::FR_ONE;
+        for (uint32_t i = 1; i < NE; i++) ypow[i] = host::mul(ypow[i - 1], pr->y);
+        fr_t* d_ypow = pr->misc + 2 * (size_t)n4;
+        ZK_CUDA(ctx, cudaMemcpyAsync(d_ypow, ypow.data(), (size_t)NE * 32, cudaMemcpyHostToDevice, ctx->stream));
+        QArgs q{};
+        q.E = pr->E; q.F = pk->fixed_ext; q.inst_ext = pr->inst_ext; q.tw_ext = dom4->tw_fwd; q.ypow = d_ypow;
+        q.delta_pow = pk->delta_pow; q.n4 = n4; q.rot = 1u << EXT_SHIFT;
+        q.n_gate = n_gate; q.n_rlc = pk->n_rlc; q.rlc_base = n_gate; q.n_advice = pk->n_advice; q.n_lookup = pk->n_lookup;
+        q.n_chunks = pk->n_chunks; q.n_perm = pk->n_perm; q.NE = NE; q.zp_base = pr->zp_base; q.zl_base = pr->zl_base;
+        q.ap_base = pr->ap_base; q.lookup_adv_base = pr->lookup_adv_base; q.usable = usable;
+        q.fx_qgate = pk->fx_qgate; q.fx_qrlc = pk->fx_qrlc; q.fx_const = pk->fx_const; q.fx_table = pk->fx_table;
+        q.fx_l0 = pk->fx_l0; q.fx_sigma = pk->fx_sigma;
+        q.cols_per_group = 16;
+        q.gamma_rlc = dev(pr->gamma_rlc); q.beta = dev(pr->beta); q.gamma = dev(pr->gamma);
+        q.zeta = dev(host::to_mont(host::FR_ZETA_CANON));
+        const uint32_t g_gate = (n_gate + pk->n_rlc + q.cols_per_group - 1) / q.cols_per_group;
+        const uint32_t groups = g_gate + pk->n_chunks + pk->n_lookup;
+        fr_t* part;
+        ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)groups * n4 * 32, (void**)&part));
+        q.part = part;
+        const uint32_t bx = (n4 + 127) / 128;
+        k_quotient_gates<<<dim3(bx, g_gate), 128, 0, ctx->stream>>>(q);
+        ZK_CHECK_LAUNCH(ctx);
+        k_quotient_perm<<<dim3(bx, pk->n_chunks), 128, 0, ctx->stream>>>(q, g_gate);
+        ZK_CHECK_LAUNCH(ctx);
+        if (pk->n_lookup) {
+            k_quotient_lookup<<<dim3(bx, pk->n_lookup), 128, 0, ctx->stream>>>(q, g_gate + pk->n_chunks);
+            ZK_CHECK_LAUNCH(ctx);
+        }
+        // 1 / (X^n - 1) on zeta * w_ext^j: X^n = zeta^n * (w_ext^n)^j, w_ext^n is a primitive 4th root of unity
+        Fr zeta = host::to_mont(host::FR_ZETA_CANON), zn = host::pow_u64(zeta, n), i4 = host::pow_u64(host::omega(k4), n);
+        Fr zh[4], cur = zn;
+        for (int r = 0; r < 4; r++) { zh[r] = host::inv(host::sub(cur, host::FR_ONE)); cur = host::mul(cur, i4); }
+        k_quotient_finish<<<bx, 128, 0, ctx->stream>>>(part, groups, n4, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_CUDA(ctx, cudaMemcpyAsync(h_coef, h_ext, (size_t)n4 * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        ZK_TRY(ntt_run(ctx, h_coef, n4, n4, h_coef, n4, k4, 1, 1, 1));
+        ZK_TRY(commit_and_write(pr, h_coef, 3, 0));
+    }
+    pr->x = pr->tr.squeeze();
+
+    // ---- opening table -----------------------------------------------------------------------------------
+    struct Opened { const fr_t* coef; int set; };
+    std::vector<Opened> polys;
+    for (uint32_t c = 0; c < pk->n_advice; c++)
+        polys.push_back({pr->P + (size_t)c * n, c < n_gate ? SET_0123 : c < n_gate + pk->n_rlc ? SET_012 : SET_0});
+    for (uint32_t f = 0; f < pk->n_fixed; f++) {
+        if (f >= pk->fx_l0 && f < pk->fx_sigma) continue;         // l_0, l_last, l_active: evaluated by the verifier
+        polys.push_back({pk->fixed_coeff + (size_t)f * n, SET_0});
+    }
+    for (uint32_t l = 0; l < pk->n_lookup; l++) {
+        polys.push_back({pr->P + (size_t)(pr->ap_base + 2 * l) * n, SET_0m1});
+        polys.push_back({pr->P + (size_t)(pr->ap_base + 2 * l + 1) * n, SET_0});
+        polys.push_back({pr->P + (size_t)(pr->zl_base + l) * n, SET_01});
+    }
+    for (uint32_t j = 0; j < pk->n_chunks; j++)
+        polys.push_back({pr->P + (size_t)(pr->zp_base + j) * n, j + 1 < pk->n_chunks ? SET_01L : SET_01});
+    polys.push_back({pr->P + (size_t)pr->r_col * n, SET_0});
+    fr_t* h_comb = pr->misc + 3 * (size_t)n4;                      // [n]
+    {
+        Fr xn = host::pow_u64(pr->x, n);
+        k_axpy3<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h_coef, n, dev(xn), dev(host::sqr(xn)), h_comb);
+        ZK_CHECK_LAUNCH(ctx);
+    }
+    polys.push_back({h_comb, SET_0});
+
+    // ---- round 5: evaluations ------------------------------------------------------------------------------
+    Fr wk = host::omega(k), winv = host::inv(wk);
+    Fr pts[6] = {host::mul(pr->x, winv), pr->x, host::mul(pr->x, wk), host::mul(pr->x, host::sqr(wk)),
+                 host::mul(pr->x, host::mul(wk, host::sqr(wk))), host::mul(pr->x, host::pow_u64(wk, usable))};
+    fr_t* pw = pr->misc + 3 * (size_t)n4 + n;                       // [6][n]
+    for (int i = 0; i < 6; i++) {
+        k_powers<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pw + (size_t)i * n, dev(pts[i]), n);
+        ZK_CHECK_LAUNCH(ctx);
+    }
+    std::vector<EvalTask> tasks;
+    for (auto& p : polys)
+        for (int r = 0; r < SET_SIZE[p.set]; r++) tasks.push_back(EvalTask{p.coef, (uint32_t)point_index(SET_ROTS[p.set][r])});
+    std::vector<Fr> evals(tasks.size());
+    {
+        EvalTask* d_tasks;
+        fr_t* d_out;
+        ZK_TRY(ws_get(ctx, "pr_tasks", tasks.size() * sizeof(EvalTask), (void**)&d_tasks));
+        ZK_TRY(ws_get(ctx, "pr_evals", tasks.size() * 32, (void**)&d_out));
+        ZK_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(EvalTask), cudaMemcpyHostToDevice, ctx->stream));
+        k_eval<<<(uint32_t)tasks.size(), 256, 0, ctx->stream>>>(d_tasks, pw, n, d_out);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_CUDA(ctx, cudaMemcpyAsync(evals.data(), d_out, tasks.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // h_comb(x) is implied by the other evaluations (the verifier recomputes it): not written
+    for (size_t i = 0; i + 1 < evals.size(); i++) pr->tr.write_scalar(evals[i]);
+
+    // ---- round 6: SHPLONK -----------------------------------------------------------------------------------
+    {
+        Fr yq = pr->tr.squeeze();
+        Fr v = pr->tr.squeeze();
+        // per set: polynomial list, combined evaluations e_t = sum_j yq^j eval_j(t)
+        std::vector<const fr_t*> set_polys[6];
+        std::vector<Fr> set_coef[6];
+        Fr set_eval[6][4];
+        for (int s = 0; s < 6; s++) for (int r = 0; r < 4; r++) set_eval[s][r] = host::FR_ZERO;
+        Fr ypow_set[6];
+        for (auto& p : ypow_set) p = host::FR_ONE;
+        size_t ei = 0;
+        for (auto& p : polys) {
+            const int s = p.set;
+            set_polys[s].push_back(p.coef);
+            set_coef[s].push_back(ypow_set[s]);
+            for (int r = 0; r < SET_SIZE[s]; r++) set_eval[s][r] = host::add(set_eval[s][r], host::mul(ypow_set[s], evals[ei + r]));
+            ei += SET_SIZE[s];
+            ypow_set[s] = host::mul(ypow_set[s], yq);
+        }
+        // f_i (coefficients), their coset evaluations, r_i and Z_i as small polynomials
+        fr_t* fbuf = pr->misc + 3 * (size_t)n4 + 7 * (size_t)n;    // [6][n] f_i, then [6][n] coset evals, acc, L
+        fr_t* fcos = fbuf + 6 * (size_t)n;
+        fr_t* acc = fcos + 6 * (size_t)n;
+        fr_t* Lp = acc + n;
+        auto small_from = [&](const std::vector<Fr>& c) {
+            SmallPoly sp{};
+            sp.len = (uint32_t)c.size();
+            for (size_t i = 0; i < c.size(); i++) sp.c[i] = dev(c[i]);
+            return sp;
+        };
+        auto poly_mul_linear = [&](std::vector<Fr> p, const Fr& root) {   // p(X) * (X - root)
+            std::vector<Fr> o(p.size() + 1, host::FR_ZERO);
+            for (size_t i = 0; i < p.size(); i++) {
+                o[i + 1] = host::add(o[i + 1], p[i]);
+                o[i] = host::sub(o[i], host::mul(p[i], root));
+            }
+            return o;
+        };
+        std::vector<Fr> rcoef[6], zcoef[6];
+        Fr zeta = host::to_mont(host::FR_ZETA_CANON);
+        Fr vpow = host::FR_ONE;
+        const fr_t** d_ptrs;
+        fr_t* d_coef;
+        size_t maxm = 0;
+        for (int s = 0; s < 6; s++) maxm = set_polys[s].size() > maxm ? set_polys[s].size() : maxm;
+        ZK_TRY(ws_get(ctx, "pr_lc_ptrs", (maxm + 8) * 8, (void**)&d_ptrs));
+        ZK_TRY(ws_get(ctx, "pr_lc_coef", (maxm + 8) * 32, (void**)&d_coef));
+        for (int s = 0; s < 6; s++) {
+            const int m = SET_SIZE[s];
+            Fr t[4];
+            for (int r = 0; r < m; r++) t[r] = pts[point_index(SET_ROTS[s][r])];
+            // Z_s(X) = prod (X - t_r);  r_s(X) = sum_r e_r * prod_{q != r} (X - t_q) / (t_r - t_q)
+            zcoef[s] = {host::FR_ONE};
+            for (int r = 0; r < m; r++) zcoef[s] = poly_mul_linear(zcoef[s], t[r]);
+            rcoef[s].assign(m, host::FR_ZERO);
+            for (int r = 0; r < m; r++) {
+                std::vector<Fr> num = {host::FR_ONE};
+                Fr den = host::FR_ONE;
+                for (int qq = 0; qq < m; qq++)
+                    if (qq != r) { num = poly_mul_linear(num, t[qq]); den = host::mul(den, host::sub(t[r], t[qq])); }
+                Fr sc = host::mul(set_eval[s][r], host::inv(den));
+                for (size_t i = 0; i < num.size(); i++) rcoef[s][i] = host::add(rcoef[s][i], host::mul(sc, num[i]));
+            }
+            if (set_polys[s].empty()) { vpow = host::mul(vpow, v); continue; }
+            ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs, set_polys[s].data(), set_polys[s].size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_CUDA(ctx, cudaMemcpyAsync(d_coef, set_coef[s].data(), set_coef[s].size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+            k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)set_polys[s].size(), n, fbuf + (size_t)s * n);
+            ZK_CHECK_LAUNCH(ctx);
+            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // d_ptrs / d_coef are reused by the next set
+            ZK_TRY(ntt_run(ctx, fbuf + (size_t)s * n, n, n, fcos + (size_t)s * n, n, k, 1, 0, 1));
+            k_shplonk_accumulate<<<(n + 127) / 128, 128, 0, ctx->stream>>>(fcos + (size_t)s * n, small_from(rcoef[s]), small_from(zcoef[s]),
+                                                                         dev(vpow), dev(zeta), dom->tw_fwd, n, acc, s == 0);
+            ZK_CHECK_LAUNCH(ctx);
+            vpow = host::mul(vpow, v);
+        }
+        ZK_TRY(ntt_run(ctx, acc, n, n, acc, n, k, 1, 1, 1));         // h'(X) coefficients
+        ZK_TRY(commit_and_write(pr, acc, 1, 0));
+        Fr u = pr->tr.squeeze();
+        // L(X) = sum_s v^s * Zc_s(u) * (f_s(X) - r_s(u)) - Z_T(u) * h'(X),  Zc_s = prod over points not in set s
+        auto eval_small = [&](const std::vector<Fr>& c, const Fr& at) {
+            Fr a = host::FR_ZERO;
+            for (size_t i = c.size(); i-- > 0;) a = host::add(host::mul(a, at), c[i]);
+            return a;
+        };
+        Fr zt = host::FR_ONE;
+        for (int i = 0; i < 6; i++) zt = host::mul(zt, host::sub(u, pts[i]));
+        std::vector<const fr_t*> lp;
+        std::vector<Fr> lc;
+        Fr cst = host::FR_ZERO;
+        vpow = host::FR_ONE;
+        for (int s = 0; s < 6; s++) {
+            if (!set_polys[s].empty()) {
+                Fr zc = host::mul(zt, host::inv(eval_small(zcoef[s], u)));
+                Fr sc = host::mul(vpow, zc);
+                lp.push_back(fbuf + (size_t)s * n);
+                lc.push_back(sc);
+                cst = host::add(cst, host::mul(sc, eval_small(rcoef[s], u)));
+            }
+            vpow = host::mul(vpow, v);
+        }
+        lp.push_back(acc);
+        lc.push_back(host::neg(zt));
+        ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(ctx, cudaMemcpyAsync(d_coef, lc.data(), lc.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+        k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)lp.size(), n, Lp);
+        ZK_CHECK_LAUNCH(ctx);
+        k_sub_const0<<<1, 1, 0, ctx->stream>>>(Lp, dev(cst));
+        ZK_CHECK_LAUNCH(ctx);
+        // L(X) / (X - u) on the coset
+        ZK_TRY(ntt_run(ctx, Lp, n, n, Lp, n, k, 1, 0, 1));
+        SmallPoly zero{};
+        zero.len = 0;
+        k_shplonk_accumulate<<<(n + 127) / 128, 128, 0, ctx->stream>>>(Lp, zero, small_from({host::neg(u), host::FR_ONE}), dev(host::FR_ONE),
+                                                                     dev(zeta), dom->tw_fwd, n, Lp, 1);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(ntt_run(ctx, Lp, n, n, Lp, n, k, 1, 1, 1));
+        ZK_TRY(commit_and_write(pr, Lp, 1, 0));
+    }
+    uint8_t* out = (uint8_t*)malloc(pr->tr.proof.size());
+    if (!out) return fail(ctx, ZKFHE_ERR_CUDA, "out of host memory");
+    memcpy(out, pr->tr.proof.data(), pr->tr.proof.size());
+    *proof_out = out;
+    *proof_len = pr->tr.proof.size();
+    pr->stage = 2;
+    return ZKFHE_OK;
+}
+
+}  // extern "C"

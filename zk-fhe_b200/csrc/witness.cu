@@ -22,35 +22,7 @@ using namespace zkfhe;
 // ---------------------------------------------------------------------------------------------
 // objects behind the opaque handles
 // ---------------------------------------------------------------------------------------------
-struct zkfhe_poly {
-    fr_t* d = nullptr;       // canonical integers in 32-byte slots, big-endian coefficient order
-    uint32_t len = 0;
-    uint64_t max_bits = 0;
-};
-
-struct DevVec {
-    fr_t* p = nullptr;
-    size_t cap = 0, size = 0;
-};
-
-template <class T> struct DevArr {
-    T* p = nullptr;
-    size_t cap = 0;
-};
-
-struct zkfhe_witness {
-    zkfhe_ctx* ctx = nullptr;
-    uint32_t lookup_bits = 8;
-    bool record = false;            // keygen / mock mode: record selectors, copies, constants
-    DevVec adv[3];
-    DevVec lk[3];
-    DevArr<uint8_t> flags[3];       // per advice cell (record mode)
-    DevArr<uint64_t> copy[3];
-    DevArr<uint64_t> lk_src[3];     // per lookup cell
-    std::vector<zkfhe_cell> make_public;
-    fr_t gamma;
-    bool have_gamma = false;
-};
+#include "witness_types.cuh"
 
 namespace zkfhe {
 

@@ -1,0 +1,105 @@
+"""Host-side handles of keygen / prove (C ABI stage: keygen + prover), for the CLI mirror and
+the tests.  `keygen(circuit)` is the reference's `keygen` subcommand; the pinning it returns has
+the schema of the reference's configs/bfv.json.
+"""
+import ctypes
+import json
+
+import numpy as np
+
+from .capi import _addr
+
+INFO_FIELDS = ("k", "n_gate0", "n_gate1", "n_rlc", "n_lookup", "n_advice", "n_perm", "n_fixed", "n_chunks",
+               "usable_rows", "max_rows", "lookup_bits", "instances", "fx_sigma", "fx_const", "fx_table")
+
+
+class ProvingKey:
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+        info = (ctypes.c_uint32 * 16)()
+        ctx._check(ctx.lib.zkfhe_pk_info(handle, info))
+        self.info = dict(zip(INFO_FIELDS, (int(x) for x in info)))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.zkfhe_pk_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    def pinning(self):
+        """dict in the schema of the reference's configs/<name>.json."""
+        need = ctypes.c_size_t()
+        self.ctx._check(self.ctx.lib.zkfhe_pk_pinning_json(self.h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        self.ctx._check(self.ctx.lib.zkfhe_pk_pinning_json(self.h, buf, need.value, None))
+        return json.loads(buf.value.decode())
+
+    def fixed(self, index, form=0):
+        """(rows, 4) uint64 Montgomery; form 0 Lagrange, 1 coefficients, 2 extended coset."""
+        n = (1 << self.info["k"]) * (4 if form == 2 else 1)
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.zkfhe_pk_download_fixed(self.h, index, form, _addr(out)))
+        return out
+
+    def fixed_commitments(self):
+        out = np.zeros((self.info["n_fixed"], 8), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.zkfhe_pk_fixed_commitments(self.h, _addr(out)))
+        return out
+
+
+TRANSCRIPT_BLAKE2B, TRANSCRIPT_POSEIDON = 0, 1
+
+
+class Prover:
+    """One proof: phase0(witness) -> gamma; (caller runs the phase-1 chip calls); finish(witness) -> bytes."""
+
+    def __init__(self, pk, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B):
+        self.pk = pk
+        self.ctx = pk.ctx
+        assert len(seed) == 32
+        self._seed = bytearray(seed)
+        h = ctypes.c_void_p()
+        self.ctx._check(self.ctx.lib.zkfhe_prove_begin(pk.h, _addr(self._seed), transcript, ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.zkfhe_prover_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    def phase0(self, witness):
+        """Commit the phase-0 advice; returns the challenge gamma as a canonical int."""
+        out = bytearray(32)
+        self.ctx._check(self.ctx.lib.zkfhe_prove_phase0(self.h, witness.h, _addr(out)))
+        from .capi import FR_MODULUS
+        return int.from_bytes(out, "little") * pow(1 << 256, -1, FR_MODULUS) % FR_MODULUS
+
+    def finish(self, witness):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self.ctx._check(self.ctx.lib.zkfhe_prove_finish(self.h, witness.h, ctypes.byref(p), ctypes.byref(n)))
+        proof = ctypes.string_at(p.value, n.value)
+        self.ctx.lib.zkfhe_proof_free(p)
+        return proof
+
+
+def prove(pk, circuit_factory, inp, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B):
+    """The reference's `prove` subcommand for one input: returns (proof bytes, circuit)."""
+    circ = circuit_factory()
+    circ.phase0(inp)
+    pr = Prover(pk, seed, transcript)
+    gamma = pr.phase0(circ.wit)
+    circ.phase1(gamma)
+    return pr.finish(circ.wit), circ
+
+
+def keygen(witness, k, unusable_rows=109):
+    """`witness`: a Witness built with record=True on the keygen input (both phases run)."""
+    h = ctypes.c_void_p()
+    witness.ctx._check(witness.ctx.lib.zkfhe_keygen(witness.h, k, unusable_rows, ctypes.byref(h)))
+    return ProvingKey(witness.ctx, h)
