@@ -248,6 +248,8 @@ typedef struct zkfhe_prover zkfhe_prover;
 int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out);
 int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_fr_out);
 int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, size_t* proof_len);
+/* Start the next proof with the same prover object (keeps its device buffers). */
+int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32);
 void zkfhe_prover_free(zkfhe_prover* pr);
 void zkfhe_proof_free(uint8_t* proof);
 
@@ -255,6 +257,12 @@ void zkfhe_proof_free(uint8_t* proof);
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last
  * NTT / MSM call: the butterfly passes for NTT, the bucket-accumulation kernel for MSM. */
 float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx);
+/* Accumulated device time per kernel category since zkfhe_timing_reset (CUDA events recorded on
+ * the context's stream around every launch of that category, so whole-proof shares can be read
+ * without a profiler).  category 0: MSM bucket accumulation (units = scalar/point pairs),
+ * 1: NTT passes (units = field elements transformed), 2: MSM sort + bucket reduction. */
+int zkfhe_timing_reset(zkfhe_ctx* ctx);
+int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, uint64_t* units);
 
 #ifdef __cplusplus
 }

@@ -52,10 +52,15 @@ class BfvCircuit:
         self.P = {}
         self.delta = None
 
-    def phase0(self, inp):
+    def upload(self, inp):
+        """The nine `Poly::from_string` calls (bfv.rs:71-79) on their own, for callers that keep
+        inputs resident in HBM between proofs."""
+        return {k: Poly.from_string(self.ctx, inp[k], self.params.Q) for k in INPUT_KEYS}
+
+    def phase0(self, inp, resident=None):
         N, Q = self.params.N, self.params.Q
         ctx, w = self.ctx, self.wit
-        un = {k: Poly.from_string(ctx, inp[k], Q) for k in INPUT_KEYS}                # :71-79
+        un = resident if resident is not None else self.upload(inp)                   # :71-79
         for k in INPUT_KEYS[:-1]:
             _assert_eq(un[k].deg(), N - 1, f"deg({k}) (examples/bfv.rs:82-89)")
         _assert_eq(un["cyclo"].deg(), N, "deg(cyclo) (examples/bfv.rs:90)")

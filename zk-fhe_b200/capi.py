@@ -56,6 +56,9 @@ _SIGNATURES = {
     "zkfhe_msm_g1": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_msm_g1_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_last_kernel_ms": (_c.c_float, [_c.c_void_p]),
+    "zkfhe_timing_reset": (_c.c_int, [_c.c_void_p]),
+    "zkfhe_timing_get": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint32),
+                                    _c.POINTER(_c.c_uint64)]),
     # stage (1a): Poly
     "zkfhe_poly_from_u64": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
     "zkfhe_poly_from_u256": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
@@ -101,6 +104,7 @@ _SIGNATURES = {
     "zkfhe_prove_begin": (_c.c_int, [_c.c_void_p, _u8p, _c.c_int, _c.POINTER(_c.c_void_p)]),
     "zkfhe_prove_phase0": (_c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     "zkfhe_prove_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_size_t)]),
+    "zkfhe_prove_reset": (_c.c_int, [_c.c_void_p, _u8p]),
     "zkfhe_prover_free": (None, [_c.c_void_p]),
     "zkfhe_proof_free": (None, [_c.c_void_p]),
     "zkfhe_witness_counts": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
@@ -208,6 +212,16 @@ class Context:
 
     def last_kernel_ms(self):
         return float(self.lib.zkfhe_last_kernel_ms(self.h))
+
+    def timing_reset(self):
+        self._check(self.lib.zkfhe_timing_reset(self.h))
+
+    def timing(self, category):
+        """(ms, spans, units) accumulated since timing_reset for a kernel category
+        (0 MSM accumulate, 1 NTT passes, 2 MSM sort + reduce)."""
+        ms, sp, un = ctypes.c_float(), ctypes.c_uint32(), ctypes.c_uint64()
+        self._check(self.lib.zkfhe_timing_get(self.h, category, ctypes.byref(ms), ctypes.byref(sp), ctypes.byref(un)))
+        return float(ms.value), int(sp.value), int(un.value)
 
     def selftest(self, n_cases=1 << 16, seed=1):
         bad = ctypes.c_uint32(0)

@@ -152,14 +152,43 @@ uint64_t zkfhe_launch_count(const zkfhe_ctx* ctx) { return ctx ? ctx->launches :
 
 float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx) {
     if (!ctx) return -1.f;
+    // dominant kernel of the last call: the accumulate kernel for MSM, the butterfly passes for NTT
     float total = 0.f;
-    for (size_t i = 0; i < ctx->ev_used; i++) {
+    for (size_t i = ctx->call_mark; i < ctx->ev_used; i++) {
+        if (ctx->ev_info[i].cat == ZK_CAT_MSM_OTHER) continue;
         if (cudaEventSynchronize(ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_pairs[i].first, ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
         total += ms;
     }
     return total;
+}
+
+int zkfhe_timing_reset(zkfhe_ctx* ctx) {
+    if (!ctx) return ZKFHE_ERR_ARG;
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ev_used = ctx->call_mark = 0;
+    return ZKFHE_OK;
+}
+
+int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, uint64_t* units) {
+    if (!ctx || category < 0 || category >= ZK_CAT_COUNT) return ZKFHE_ERR_ARG;
+    float total = 0.f;
+    uint32_t cnt = 0;
+    uint64_t un = 0;
+    for (size_t i = 0; i < ctx->ev_used; i++) {
+        if (ctx->ev_info[i].cat != category) continue;
+        ZK_CUDA(ctx, cudaEventSynchronize(ctx->ev_pairs[i].second));
+        float t = 0.f;
+        ZK_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev_pairs[i].first, ctx->ev_pairs[i].second));
+        total += t;
+        cnt++;
+        un += ctx->ev_info[i].units;
+    }
+    if (ms) *ms = total;
+    if (spans) *spans = cnt;
+    if (units) *units = un;
+    return ZKFHE_OK;
 }
 
 int zkfhe_selftest(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches) {

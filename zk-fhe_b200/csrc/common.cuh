@@ -45,9 +45,13 @@ struct zkfhe_ctx {
     uint32_t srs_k = 0;
     std::map<std::string, zkfhe::DevBuf> ws;     // named, grow-only workspaces
     // CUDA-event pairs bracketing the dominant kernel(s) of the last NTT / MSM call
+    // (a pool: spans accumulate until zkfhe_timing_reset; `call_mark` is where the last call started)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
-    size_t ev_used = 0;
+    struct SpanInfo { int cat; uint64_t units; };
+    std::vector<SpanInfo> ev_info;
+    size_t ev_used = 0, call_mark = 0;
 };
+enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_COUNT = 3 };
 
 namespace zkfhe {
 
@@ -84,13 +88,19 @@ inline int fail(zkfhe_ctx* ctx, int code, const char* fmt, ...) {
         if (rc__ != ZKFHE_OK) return rc__; \
     } while (0)
 
-inline int timed_begin(zkfhe_ctx* ctx) {
+inline void timed_call_start(zkfhe_ctx* ctx) {
+    if (ctx->ev_used > 8192) ctx->ev_used = 0;      // bounded pool: old spans are dropped
+    ctx->call_mark = ctx->ev_used;
+}
+inline int timed_begin(zkfhe_ctx* ctx, int cat = 0, uint64_t units = 0) {
     if (ctx->ev_used == ctx->ev_pairs.size()) {
         cudaEvent_t a, b;
         ZK_CUDA(ctx, cudaEventCreate(&a));
         ZK_CUDA(ctx, cudaEventCreate(&b));
         ctx->ev_pairs.emplace_back(a, b);
+        ctx->ev_info.push_back({cat, units});
     }
+    ctx->ev_info[ctx->ev_used] = {cat, units};
     ZK_CUDA(ctx, cudaEventRecord(ctx->ev_pairs[ctx->ev_used].first, ctx->stream));
     return ZKFHE_OK;
 }

@@ -392,22 +392,26 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     size_t smem = (size_t)NB * 4;
     if (smem > 48 * 1024)
         ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->ev_used = 0;
+    timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
         const fr_t* sc = d_scalars + (uint64_t)done * stride;
+        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
         k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs);
         ZK_CHECK_LAUNCH(ctx);
-        ZK_TRY(timed_begin(ctx));
+        ZK_TRY(timed_end(ctx));
+        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
         dim3 grid((uint32_t)((max_thr + 127) / 128), nb);
         k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, boff, soff, sorted, max_refs, partial, max_segs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
+        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
         dim3 fgrid((groups + 127) / 128, nb);
         k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, boff, soff, partial, max_segs, grp);
         ZK_CHECK_LAUNCH(ctx);
         k_msm_final<<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
         ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(timed_end(ctx));
     }
     return ZKFHE_OK;
 }

@@ -181,8 +181,8 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
     p.n_inv = dom->n_inv;
     p.zeta = fr_t{ZKFHE_FR_ZETA_MONT};
     p.zeta2 = fr_t{ZKFHE_FR_ZETA2_MONT};
-    ctx->ev_used = 0;
-    ZK_TRY(timed_begin(ctx));
+    timed_call_start(ctx);
+    ZK_TRY(timed_begin(ctx, ZK_CAT_NTT, (uint64_t)batch << log_n));
     if (log_n <= 11) {
         p.in = d_in; p.out = d_out; p.in_stride = in_stride; p.out_stride = out_stride;
         p.log_r = log_n; p.log_l = 0; p.mode = 1; p.in_len = in_len;

@@ -501,6 +501,16 @@ void zkfhe_prover_free(zkfhe_prover* pr) {
 
 void zkfhe_proof_free(uint8_t* proof) { free(proof); }
 
+// Reuse a prover object (and its ~1 GB of device buffers) for the next proof.
+int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32) {
+    if (!pr || !seed32) return ZKFHE_ERR_ARG;
+    const int kind = pr->tr.kind;
+    pr->tr = host::Transcript(kind);
+    pr->rng = ChaCha20(seed32);
+    pr->stage = 0;
+    return ZKFHE_OK;
+}
+
 int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out) {
     if (!pk || !seed32 || !out) return ZKFHE_ERR_ARG;
     zkfhe_ctx* ctx = pk->ctx;

@@ -387,7 +387,8 @@ static inline uint32_t blocks_for(uint32_t n, uint32_t t = 128) { return (n + t 
 static int poly_alloc(zkfhe_ctx* ctx, uint32_t len, uint64_t max_bits, zkfhe_poly** out) {
     zkfhe_poly* p = new (std::nothrow) zkfhe_poly();
     if (!p) return fail(ctx, ZKFHE_ERR_CUDA, "out of host memory");
-    cudaError_t e = cudaMalloc(&p->d, (size_t)(len ? len : 1) * sizeof(fr_t));
+    p->ctx = ctx;    // stream-ordered allocation: no device-wide synchronisation on alloc / free
+    cudaError_t e = cudaMallocAsync((void**)&p->d, (size_t)(len ? len : 1) * sizeof(fr_t), ctx->stream);
     if (e != cudaSuccess) {
         delete p;
         return fail(ctx, ZKFHE_ERR_CUDA, "cudaMalloc(poly): %s", cudaGetErrorString(e));
@@ -614,7 +615,10 @@ int zkfhe_poly_download(zkfhe_ctx* ctx, const zkfhe_poly* p, uint64_t* h_out) {
 
 void zkfhe_poly_free(zkfhe_poly* p) {
     if (!p) return;
-    if (p->d) cudaFree(p->d);
+    if (p->d) {
+        if (p->ctx) { cudaSetDevice(p->ctx->device); cudaFreeAsync(p->d, p->ctx->stream); }
+        else cudaFree(p->d);
+    }
     delete p;
 }
 

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 struct zkfhe_poly {
+    zkfhe_ctx* ctx = nullptr;
     zkfhe::fr_t* d = nullptr;       // canonical integers in 32-byte slots, big-endian coefficient order
     uint32_t len = 0;
     uint64_t max_bits = 0;

@@ -73,6 +73,12 @@ class Prover:
             pass
         self.h = None
 
+    def reset(self, seed):
+        """Next proof with the same device buffers."""
+        assert len(seed) == 32
+        self._seed = bytearray(seed)
+        self.ctx._check(self.ctx.lib.zkfhe_prove_reset(self.h, _addr(self._seed)))
+
     def phase0(self, witness):
         """Commit the phase-0 advice; returns the challenge gamma as a canonical int."""
         out = bytearray(32)
