@@ -95,6 +95,8 @@ int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t
  * GPU from an explicit tau (Fr, Montgomery) and loaded as by zkfhe_load_srs.  The bases are also
  * copied to the host when the output pointers are non-NULL (n x 64 bytes each).  INSECURE. */
 int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t* h_g_out, uint8_t* h_g_lagrange_out);
+/* Make `dst` use the resident commitment-key tables of `src` (same GPU; `src` must outlive `dst`). */
+int zkfhe_share_srs(zkfhe_ctx* dst, const zkfhe_ctx* src);
 /* In place: canonical 256-bit integers -> Montgomery Fr (to_montgomery = 1) or back (0). */
 int zkfhe_fr_convert_dev(zkfhe_ctx* ctx, uint8_t* d_data, uint64_t count, int to_montgomery);
 /* out[b] = sum_i scalars[b][i] * basis[i], b < batch; scalars are batch x 2^k Fr. */
@@ -245,9 +247,17 @@ int zkfhe_pk_fixed_commitments(const zkfhe_pk* pk, uint8_t* h_out);
  * The proof is a malloc'd byte string (free with zkfhe_proof_free): commitments as canonical
  * uncompressed points (64 bytes), scalars canonical little-endian (32 bytes), in round order. */
 typedef struct zkfhe_prover zkfhe_prover;
-int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out);
+/* `ctx` is the context (stream) the proof runs on; it may differ from the one keygen ran on (same
+ * GPU), so several proofs can be in flight on one GPU, one context per host thread, all sharing one
+ * proving key and -- via zkfhe_share_srs -- one copy of the commitment-key tables. */
+int zkfhe_prove_begin(zkfhe_ctx* ctx, zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out);
 int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_fr_out);
 int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, size_t* proof_len);
+/* Host wall-clock (ms) of the rounds of the last proof; each round ends with a synchronising
+ * read-back of its commitments, so these are true latencies: [0] phase-0 commit, [1] phase-1 advice
+ * commit, [2] lookup permutations, [3] grand products, [4] quotient, [5] evaluations, [6] SHPLONK
+ * quotient commit, [7] final opening commit. */
+int zkfhe_prover_round_ms(const zkfhe_prover* pr, double out[8]);
 /* Start the next proof with the same prover object (keeps its device buffers). */
 int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32);
 void zkfhe_prover_free(zkfhe_prover* pr);

@@ -101,10 +101,12 @@ _SIGNATURES = {
     "zkfhe_pk_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint32)]),
     "zkfhe_pk_download_fixed": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _u8p]),
     "zkfhe_pk_fixed_commitments": (_c.c_int, [_c.c_void_p, _u8p]),
-    "zkfhe_prove_begin": (_c.c_int, [_c.c_void_p, _u8p, _c.c_int, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_prove_begin": (_c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_int, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_share_srs": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "zkfhe_prove_phase0": (_c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     "zkfhe_prove_finish": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_size_t)]),
     "zkfhe_prove_reset": (_c.c_int, [_c.c_void_p, _u8p]),
+    "zkfhe_prover_round_ms": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_double)]),
     "zkfhe_prover_free": (None, [_c.c_void_p]),
     "zkfhe_proof_free": (None, [_c.c_void_p]),
     "zkfhe_witness_counts": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
@@ -252,6 +254,12 @@ class Context:
         self._check(self.lib.zkfhe_srs_setup(self.h, k, _addr(t), _addr(g), _addr(gl)))
         self.srs_k = k
         return (bytes(g), bytes(gl)) if want_host_copy else None
+
+    def share_srs(self, other):
+        """Use `other`'s resident commitment-key tables (same GPU); `other` must stay alive."""
+        self._check(self.lib.zkfhe_share_srs(self.h, other.h))
+        self.srs_k = other.srs_k
+        self._srs_owner = other
 
     def fr_convert_dev(self, d_ptr, count, to_montgomery=True):
         self._check(self.lib.zkfhe_fr_convert_dev(self.h, d_ptr, count, int(to_montgomery)))

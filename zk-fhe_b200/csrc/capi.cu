@@ -124,7 +124,7 @@ void zkfhe_destroy(zkfhe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->domains) { cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); }
-    for (auto& b : ctx->basis) if (b.table) cudaFree(b.table);
+    for (auto& b : ctx->basis) if (b.table && !b.shared) cudaFree(b.table);
     for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -155,7 +155,7 @@ float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx) {
     // dominant kernel of the last call: the accumulate kernel for MSM, the butterfly passes for NTT
     float total = 0.f;
     for (size_t i = ctx->call_mark; i < ctx->ev_used; i++) {
-        if (ctx->ev_info[i].cat == ZK_CAT_MSM_OTHER) continue;
+        if (ctx->ev_info[i].cat >= ZK_CAT_MSM_OTHER) continue;
         if (cudaEventSynchronize(ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_pairs[i].first, ctx->ev_pairs[i].second) != cudaSuccess) return -1.f;
@@ -268,6 +268,19 @@ int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t
     if (h_g_lagrange_out)
         ZK_CUDA(ctx, cudaMemcpyAsync(h_g_lagrange_out, d + ((size_t)1 << k), bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_share_srs(zkfhe_ctx* dst, const zkfhe_ctx* src) {
+    if (!dst || !src) return ZKFHE_ERR_ARG;
+    if (dst->device != src->device) return fail(dst, ZKFHE_ERR_ARG, "share_srs: contexts are on different devices");
+    if (src->srs_k == 0) return fail(dst, ZKFHE_ERR_STATE, "share_srs: the source context has no SRS");
+    for (int i = 0; i < 2; i++) {
+        if (dst->basis[i].table && !dst->basis[i].shared) cudaFree(dst->basis[i].table);
+        dst->basis[i] = src->basis[i];
+        dst->basis[i].shared = true;
+    }
+    dst->srs_k = src->srs_k;
     return ZKFHE_OK;
 }
 

@@ -24,6 +24,7 @@ struct MsmBasis {
     g1_affine* table = nullptr;   // [W][n] : table[w*n + i] = 2^(c*w) * P_i  (affine, Montgomery)
     uint32_t log_n = 0, c = 0, W = 0;
     bool loaded = false;
+    bool shared = false;          // table owned by another context (zkfhe_share_srs)
 };
 
 struct NttDomain {
@@ -51,7 +52,7 @@ struct zkfhe_ctx {
     std::vector<SpanInfo> ev_info;
     size_t ev_used = 0, call_mark = 0;
 };
-enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_COUNT = 3 };
+enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4, ZK_CAT_COUNT = 5 };
 
 namespace zkfhe {
 

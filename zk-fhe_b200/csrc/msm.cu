@@ -27,7 +27,9 @@
 
 namespace zkfhe {
 
-static constexpr uint32_t SEG = 64;          // point references summed by one thread
+// point references summed by one accumulate thread: long slices for big batches (fewer partial sums),
+// short ones when only a few columns are committed (shorter dependent chain, more threads)
+static inline uint32_t pick_seg(uint32_t batch) { return batch < 32 ? 16 : 64; }
 
 // ---- fixed-base table ---------------------------------------------------------------------
 __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint32_t n, uint32_t c, uint32_t W) {
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
 // and writes one partial sum per bucket it touches to slot rank[b] + t.  Slots are strictly
 // increasing along the list, so they never collide; bucket b's partials are exactly the slots
 // rank[b] + t for t in [boff[b]/SEG, (boff[b+1]-1)/SEG].
-__global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restrict__ table, uint32_t c,
+__global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restrict__ table, uint32_t c, uint32_t SEG,
                                                         const uint32_t* __restrict__ bucket_off,
                                                         const uint32_t* __restrict__ rank_in,
                                                         const uint32_t* __restrict__ sorted, uint64_t sorted_stride,
@@ -198,10 +200,46 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const g1_affine* __restr
 // several places, so keeping one copy keeps them inside the instruction cache.
 __device__ __noinline__ void xyzz_add_ni(g1_xyzz& acc, const g1_xyzz& p) { xyzz_add(acc, p); }
 
+// Reduction, level 0: bound the partial-sum list of every bucket.  Witness columns repeat a few
+// small values thousands of times, so one bucket can own up to n/SEG consecutive partial sums; a
+// serial walk over them would put a hundred dependent point additions on one thread.  Slices are
+// grouped SUP at a time: thread s of a column owns level-2 slot s = rank[b] + u (u = super-slice
+// index) and adds the <= SUP level-1 partials of bucket b inside super-slice u.  Same slot
+// arithmetic as level 1 with SEG*SUP in place of SEG, so k_msm_fold reads the result unchanged.
+static constexpr uint32_t SUP = 16;
+__global__ void __launch_bounds__(128) k_msm_combine(uint32_t c, uint32_t SEG, const uint32_t* __restrict__ bucket_off,
+                                                     const uint32_t* __restrict__ rank_in,
+                                                     const g1_xyzz* __restrict__ partial, uint64_t partial_stride,
+                                                     g1_xyzz* partial2, uint64_t partial2_stride) {
+    const uint32_t NB = 1u << (c - 1);
+    const uint32_t col = blockIdx.y, s2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
+    const uint32_t total = boff[NB];
+    if (total == 0) return;
+    const uint32_t SS = SEG * SUP;
+    if (s2 > rnk[NB] + (total - 1) / SS) return;         // beyond the last used slot
+    // largest b with key(b) = rank[b] + boff[b]/SS <= s2  (key is non-decreasing, key(0) = 0)
+    uint32_t lo = 0, hi = NB;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (rnk[mid] + boff[mid] / SS <= s2) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo, e0 = boff[b], e1 = boff[b + 1];
+    if (e1 == e0) return;
+    const uint32_t u = s2 - rnk[b];
+    if (u < e0 / SS || u > (e1 - 1) / SS) return;        // a gap slot: nothing maps here
+    const uint32_t t0 = max(e0 / SEG, u * SUP), t1 = min((e1 - 1) / SEG, u * SUP + SUP - 1);
+    const g1_xyzz* part = partial + (uint64_t)col * partial_stride + rnk[b];
+    g1_xyzz acc = xyzz_load(part + t0);
+    for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add_ni(acc, xyzz_load(part + t));
+    xyzz_store(partial2 + (uint64_t)col * partial2_stride + s2, acc);
+}
+
 // Reduction, level 1: one thread per group of FOLD consecutive buckets.  Folds the partial sums of
 // each bucket and runs the running-sum trick inside the group:
 //   S_g = sum_b B_b,   A_g = sum_b (b - lo + 1) B_b      (so sum_b (b+1) B_b = A_g + lo * S_g)
-__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, const uint32_t* __restrict__ bucket_off,
+__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uint32_t SEG, const uint32_t* __restrict__ bucket_off,
                                                   const uint32_t* __restrict__ rank_in,
                                                   const g1_xyzz* __restrict__ partial, uint64_t partial_stride,
                                                   g1_xyzz* group_out /* [col][groups][2] */) {
@@ -231,8 +269,9 @@ __global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, con
 //   total = sum_g A_g + fold * sum_g g * S_g,   sum_g g * S_g = sum_{g>=1} U_g,  U_g = sum_{h>=g} S_h
 // U is a suffix scan in shared memory (log2(groups) steps), the two sums are tree reductions.
 extern __shared__ uint4 msm_final_smem[];
-__global__ void __launch_bounds__(1024) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
-                                                    g1_affine* out) {
+template <uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
+                                                       g1_affine* out) {
     g1_xyzz* U = reinterpret_cast<g1_xyzz*>(msm_final_smem);     // [groups]
     g1_xyzz* A = U + groups;                                      // [groups]
     const uint32_t col = blockIdx.x, t = threadIdx.x;
@@ -251,14 +290,14 @@ __global__ void __launch_bounds__(1024) k_msm_final(uint32_t groups, uint32_t lo
     }
     if (t == 0) xyzz_store(&U[0], xyzz_identity());               // the g = 0 term has weight 0
     __syncthreads();
+    // two tree reductions side by side: threads [0, stride) fold U, threads [stride, 2*stride) fold A
     for (uint32_t stride = groups >> 1; stride > 0; stride >>= 1) {
-        if (t < stride) {
-            g1_xyzz a = xyzz_load(&U[t]);
-            xyzz_add_ni(a, xyzz_load(&U[t + stride]));
-            xyzz_store(&U[t], a);
-            g1_xyzz b = xyzz_load(&A[t]);
-            xyzz_add_ni(b, xyzz_load(&A[t + stride]));
-            xyzz_store(&A[t], b);
+        if (t < 2 * stride) {          // within a level, X[i] is read and written by thread i only
+            g1_xyzz* X = t < stride ? U : A;
+            const uint32_t i = t < stride ? t : t - stride;
+            g1_xyzz a = xyzz_load(&X[i]);
+            xyzz_add_ni(a, xyzz_load(&X[i + stride]));
+            xyzz_store(&X[i], a);
         }
         __syncthreads();
     }
@@ -342,7 +381,8 @@ static uint32_t pick_window(uint32_t log_n) {
 
 int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n) {
     MsmBasis& B = ctx->basis[which];
-    if (B.table) { ZK_CUDA(ctx, cudaFree(B.table)); B.table = nullptr; B.loaded = false; }
+    if (B.table && !B.shared) ZK_CUDA(ctx, cudaFree(B.table));
+    B.table = nullptr; B.loaded = false; B.shared = false;
     B.log_n = log_n;
     B.c = pick_window(log_n);
     B.W = (255 + B.c - 1) / B.c;
@@ -365,6 +405,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     if (batch == 0) return ZKFHE_OK;
     const uint32_t n = 1u << log_n, c = B.c, W = B.W, NB = 1u << (c - 1);
     const uint64_t max_refs = (uint64_t)n * W;
+    const uint32_t SEG = pick_seg(batch);
     const uint64_t max_thr = (max_refs + SEG - 1) / SEG;     // accumulate threads per column
     const uint64_t max_segs = NB + max_thr;                  // partial slots: rank[b] + t
     // bound the workspace: process the batch in chunks
@@ -379,19 +420,25 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     ZK_TRY(ws_get(ctx, "msm_soff", (size_t)chunk * (NB + 1) * 4, (void**)&soff));
     ZK_TRY(ws_get(ctx, "msm_sorted", (size_t)chunk * max_refs * 4, (void**)&sorted));
     ZK_TRY(ws_get(ctx, "msm_partial", (size_t)chunk * max_segs * sizeof(g1_xyzz), (void**)&partial));
+    const uint64_t max_segs2 = NB + (max_thr + SUP - 1) / SUP + 1;      // level-2 slots: rank[b] + super-slice
+    g1_xyzz* partial2;
+    ZK_TRY(ws_get(ctx, "msm_partial2", (size_t)chunk * max_segs2 * sizeof(g1_xyzz), (void**)&partial2));
     // reduction shape: groups of 2^log_fold buckets, one thread per group in the final CTA
-    uint32_t log_fold = 4;
-    while ((NB >> log_fold) == 0) log_fold--;
-    while ((NB >> log_fold) > 1024) log_fold++;
+    // (a few columns: narrow groups and a 1024-thread final CTA keep the dependent chain short;
+    //  many columns: wide groups, the kernels are throughput-bound anyway)
+    uint32_t log_fold = batch < 32 ? 3 : 4;
+    while (log_fold && (NB >> log_fold) == 0) log_fold--;
+    while ((NB >> log_fold) > (batch < 32 ? 512u : 256u)) log_fold++;
     const uint32_t groups = NB >> log_fold;
     g1_xyzz* grp;
     ZK_TRY(ws_get(ctx, "msm_groups", (size_t)chunk * groups * 2 * sizeof(g1_xyzz), (void**)&grp));
     const size_t fsmem = (size_t)groups * 2 * sizeof(g1_xyzz);
-    if (fsmem > 48 * 1024)
-        ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    // function attributes are process-wide: always raise them to the fixed maximum any call can need,
+    // never to this call's size (several contexts may be launching from different host threads)
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * (int)sizeof(g1_xyzz)));
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 2 * (int)sizeof(g1_xyzz)));
     size_t smem = (size_t)NB * 4;
-    if (smem > 48 * 1024)
-        ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
@@ -402,14 +449,20 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
         dim3 grid((uint32_t)((max_thr + 127) / 128), nb);
-        k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, boff, soff, sorted, max_refs, partial, max_segs);
+        k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, SEG, boff, soff, sorted, max_refs, partial, max_segs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
-        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
-        dim3 fgrid((groups + 127) / 128, nb);
-        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, boff, soff, partial, max_segs, grp);
+        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FOLD, 0));
+        dim3 cgrid((uint32_t)((max_segs2 + 127) / 128), nb);
+        k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2);
         ZK_CHECK_LAUNCH(ctx);
-        k_msm_final<<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
+        dim3 fgrid((groups + 127) / 128, nb);
+        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG * SUP, boff, soff, partial2, max_segs2, grp);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(timed_end(ctx));
+        ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
+        if (groups <= 256) k_msm_final<256><<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
+        else k_msm_final<512><<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
     }

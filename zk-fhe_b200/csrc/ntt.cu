@@ -159,9 +159,8 @@ static int launch_pass(zkfhe_ctx* ctx, const NttPass& p, uint32_t tiles, uint32_
     uint32_t T = 1u << (p.log_r + p.log_l);
     uint32_t threads = T / 2 < 32 ? 32 : (T / 2 > 1024 ? 1024 : T / 2);
     size_t smem = (size_t)T * sizeof(fr_t);
-    if (smem > 48 * 1024) {
-        ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    // process-wide attribute: always the fixed maximum (2048-element tile), never this call's size
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int)sizeof(fr_t)));
     dim3 grid(tiles, batch);
     k_ntt_pass<<<grid, threads, smem, ctx->stream>>>(p);
     ZK_CHECK_LAUNCH(ctx);

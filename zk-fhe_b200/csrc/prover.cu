@@ -19,6 +19,7 @@
 //   4  W h_0, h_1, h_2 (quotient pieces)       C x
 //   5  W evaluations at x * w^rot (order = opening table)
 //   6  SHPLONK: C y', C v, W [h'], C u, W [L/(X-u)]
+#include <chrono>
 #include <cstring>
 #include <new>
 #include "prover.cuh"
@@ -417,6 +418,31 @@ __global__ void k_shplonk_accumulate(const fr_t* f_coset, SmallPoly r, SmallPoly
     fr_t v = mul(mul(sub(fe_load(f_coset + row), small_eval(r, x)), inv(small_eval(z, x))), scale);
     fe_store(acc + row, first ? v : add(fe_load(acc + row), v));
 }
+// All rotation sets at once: acc[row] = sum_s scale_s * (f_s[row] - r_s(c)) / Z_s(c), one inversion per row
+// (Montgomery's trick over the six denominators).
+struct ShplonkSets { SmallPoly r[6], z[6]; fr_t scale[6]; };
+__global__ void k_shplonk_quotient(const fr_t* f_coset /*[6][n]*/, const ShplonkSets S, fr_t zeta, const fr_t* tw, uint32_t n, fr_t* acc) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fr_t x = mul(zeta, fe_load(tw + row));
+    fr_t num[6], den[6], pre[6];
+    fr_t run = fe_one<FR>();
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        num[s] = mul(sub(fe_load(f_coset + (size_t)s * n + row), small_eval(S.r[s], x)), S.scale[s]);
+        den[s] = small_eval(S.z[s], x);
+        pre[s] = run;
+        run = mul(run, den[s]);
+    }
+    fr_t irun = inv(run);
+    fr_t out = fe_zero<FR>();
+#pragma unroll
+    for (int s = 5; s >= 0; s--) {
+        out = add(out, mul(num[s], mul(irun, pre[s])));
+        irun = mul(irun, den[s]);
+    }
+    fe_store(acc + row, out);
+}
 // h_comb = sum_i x^(n*i) h_i
 __global__ void k_axpy3(const fr_t* h, uint32_t n, fr_t s1, fr_t s2, fr_t* out) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +463,17 @@ struct zkfhe_prover {
     uint32_t C_all = 0, ap_base = 0, zp_base = 0, zl_base = 0, r_col = 0, lookup_adv_base = 0;
     fr_t *P = nullptr, *E = nullptr, *inst = nullptr, *inst_ext = nullptr, *blind = nullptr, *misc = nullptr;
     Fr gamma_rlc, theta, beta, gamma, y, x;
-    float ms_commit = 0, ms_ntt = 0, ms_quotient = 0, ms_open = 0;
+    // host wall-clock at the end of each round (every round ends with a synchronising commitment
+    // read-back, so these are true round latencies): [0] phase-0 commit, [1] phase-1 advice,
+    // [2] lookup permutations, [3] grand products, [4] quotient, [5] evaluations, [6] h' commit, [7] end
+    double round_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::chrono::steady_clock::time_point t_mark;
+    void mark_start() { t_mark = std::chrono::steady_clock::now(); }
+    void mark(int i) {
+        auto now = std::chrono::steady_clock::now();
+        round_ms[i] = std::chrono::duration<double, std::milli>(now - t_mark).count();
+        t_mark = now;
+    }
     zkfhe_prover(const uint8_t seed[32], int kind) : tr(kind), rng(seed) {}
 };
 
@@ -511,9 +547,9 @@ int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32) {
     return ZKFHE_OK;
 }
 
-int zkfhe_prove_begin(zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out) {
-    if (!pk || !seed32 || !out) return ZKFHE_ERR_ARG;
-    zkfhe_ctx* ctx = pk->ctx;
+int zkfhe_prove_begin(zkfhe_ctx* ctx, zkfhe_pk* pk, const uint8_t* seed32, int transcript_kind, zkfhe_prover** out) {
+    if (!ctx || !pk || !seed32 || !out) return ZKFHE_ERR_ARG;
+    if (ctx->device != pk->ctx->device) return fail(ctx, ZKFHE_ERR_ARG, "prove_begin: the proving key lives on another device");
     if (transcript_kind != host::TRANSCRIPT_BLAKE2B && transcript_kind != host::TRANSCRIPT_POSEIDON)
         return fail(ctx, ZKFHE_ERR_ARG, "prove_begin: unknown transcript kind %d", transcript_kind);
     if (ctx->srs_k != pk->k) return fail(ctx, ZKFHE_ERR_STATE, "prove_begin: SRS for k=%u is not loaded", pk->k);
@@ -551,6 +587,8 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     zkfhe_ctx* ctx = pr->ctx;
     zkfhe_pk* pk = pr->pk;
     if (pr->stage != 0) return fail(ctx, ZKFHE_ERR_STATE, "prove_phase0: called out of order");
+    if (w->ctx != ctx) return fail(ctx, ZKFHE_ERR_ARG, "prove_phase0: witness and prover belong to different contexts");
+    pr->mark_start();
     if (w->adv[0].size != pk->cells[0] || w->make_public.size() != pk->instances)
         return fail(ctx, ZKFHE_ERR_ARG, "prove_phase0: witness shape differs from the proving key (%zu cells, key has %llu)",
                     w->adv[0].size, (unsigned long long)pk->cells[0]);
@@ -580,6 +618,7 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     pr->gamma_rlc = pr->tr.squeeze();
     memcpy(h_gamma_out, pr->gamma_rlc.l, 32);
     pr->stage = 1;
+    pr->mark(0);
     return ZKFHE_OK;
 }
 
@@ -588,6 +627,8 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     zkfhe_ctx* ctx = pr->ctx;
     zkfhe_pk* pk = pr->pk;
     if (pr->stage != 1) return fail(ctx, ZKFHE_ERR_STATE, "prove_finish: zkfhe_prove_phase0 must run first");
+    if (w->ctx != ctx) return fail(ctx, ZKFHE_ERR_ARG, "prove_finish: witness and prover belong to different contexts");
+    pr->mark_start();
     size_t lookups = 0;
     for (int c = 0; c < 3; c++) lookups += w->lk[c].size;
     if (w->adv[1].size != pk->cells[1] || w->adv[2].size != pk->cells[2] || lookups != pk->lookups || w->lk[1].size != lookups)
@@ -622,6 +663,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(commit_and_write(pr, pr->P + (size_t)pk->n_gate0 * n, pk->n_advice - pk->n_gate0, 1));
     }
     pr->theta = pr->tr.squeeze();
+    pr->mark(1);
 
     // ---- round 2: lookup permuted columns -----------------------------------------------------------
     {
@@ -639,6 +681,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
             return fail(ctx, ZKFHE_ERR_UNSATISFIED, "prove: a lookup cell is outside the table [0, 2^%u)", pk->lookup_bits);
         }
     }
+    pr->mark(2);
     pr->beta = pr->tr.squeeze();
     pr->gamma = pr->tr.squeeze();
 
@@ -668,6 +711,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->zp_base * n, nz + 1, 1));
     }
     pr->y = pr->tr.squeeze();
+    pr->mark(3);
 
     // ---- round 4: quotient -----------------------------------------------------------------------------
     fr_t* h_ext = pr->misc;                       // [4n]
@@ -720,6 +764,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(commit_and_write(pr, h_coef, 3, 0));
     }
     pr->x = pr->tr.squeeze();
+    pr->mark(4);
 
     // ---- opening table -----------------------------------------------------------------------------------
     struct Opened { const fr_t* coef; int set; };
@@ -775,6 +820,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
 
     // ---- round 6: SHPLONK -----------------------------------------------------------------------------------
     {
+        pr->mark(5);
         Fr yq = pr->tr.squeeze();
         Fr v = pr->tr.squeeze();
         // per set: polynomial list, combined evaluations e_t = sum_j yq^j eval_j(t)
@@ -817,10 +863,11 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         Fr vpow = host::FR_ONE;
         const fr_t** d_ptrs;
         fr_t* d_coef;
-        size_t maxm = 0;
-        for (int s = 0; s < 6; s++) maxm = set_polys[s].size() > maxm ? set_polys[s].size() : maxm;
-        ZK_TRY(ws_get(ctx, "pr_lc_ptrs", (maxm + 8) * 8, (void**)&d_ptrs));
-        ZK_TRY(ws_get(ctx, "pr_lc_coef", (maxm + 8) * 32, (void**)&d_coef));
+        size_t total_m = 0, set_off[6];
+        for (int s = 0; s < 6; s++) { set_off[s] = total_m; total_m += set_polys[s].size(); }
+        ZK_TRY(ws_get(ctx, "pr_lc_ptrs", (total_m + 8) * 8, (void**)&d_ptrs));
+        ZK_TRY(ws_get(ctx, "pr_lc_coef", (total_m + 8) * 32, (void**)&d_coef));
+        ShplonkSets sets{};
         for (int s = 0; s < 6; s++) {
             const int m = SET_SIZE[s];
             Fr t[4];
@@ -837,20 +884,26 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
                 Fr sc = host::mul(set_eval[s][r], host::inv(den));
                 for (size_t i = 0; i < num.size(); i++) rcoef[s][i] = host::add(rcoef[s][i], host::mul(sc, num[i]));
             }
-            if (set_polys[s].empty()) { vpow = host::mul(vpow, v); continue; }
-            ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs, set_polys[s].data(), set_polys[s].size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            ZK_CUDA(ctx, cudaMemcpyAsync(d_coef, set_coef[s].data(), set_coef[s].size() * 32, cudaMemcpyHostToDevice, ctx->stream));
-            k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)set_polys[s].size(), n, fbuf + (size_t)s * n);
-            ZK_CHECK_LAUNCH(ctx);
-            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // d_ptrs / d_coef are reused by the next set
-            ZK_TRY(ntt_run(ctx, fbuf + (size_t)s * n, n, n, fcos + (size_t)s * n, n, k, 1, 0, 1));
-            k_shplonk_accumulate<<<(n + 127) / 128, 128, 0, ctx->stream>>>(fcos + (size_t)s * n, small_from(rcoef[s]), small_from(zcoef[s]),
-                                                                         dev(vpow), dev(zeta), dom->tw_fwd, n, acc, s == 0);
-            ZK_CHECK_LAUNCH(ctx);
+            sets.r[s] = small_from(rcoef[s]);
+            sets.z[s] = small_from(zcoef[s]);
+            sets.scale[s] = dev(set_polys[s].empty() ? host::FR_ZERO : vpow);
             vpow = host::mul(vpow, v);
+            if (set_polys[s].empty()) {
+                ZK_CUDA(ctx, cudaMemsetAsync(fbuf + (size_t)s * n, 0, (size_t)n * 32, ctx->stream));
+                continue;
+            }
+            ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs + set_off[s], set_polys[s].data(), set_polys[s].size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_CUDA(ctx, cudaMemcpyAsync(d_coef + set_off[s], set_coef[s].data(), set_coef[s].size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+            k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs + set_off[s], d_coef + set_off[s], (uint32_t)set_polys[s].size(), n,
+                                                                fbuf + (size_t)s * n);
+            ZK_CHECK_LAUNCH(ctx);
         }
+        ZK_TRY(ntt_run(ctx, fbuf, n, n, fcos, n, k, 6, 0, 1));          // all six f_s on the coset zeta*H
+        k_shplonk_quotient<<<(n + 127) / 128, 128, 0, ctx->stream>>>(fcos, sets, dev(zeta), dom->tw_fwd, n, acc);
+        ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(ntt_run(ctx, acc, n, n, acc, n, k, 1, 1, 1));         // h'(X) coefficients
         ZK_TRY(commit_and_write(pr, acc, 1, 0));
+        pr->mark(6);
         Fr u = pr->tr.squeeze();
         // L(X) = sum_s v^s * Zc_s(u) * (f_s(X) - r_s(u)) - Z_T(u) * h'(X),  Zc_s = prod over points not in set s
         auto eval_small = [&](const std::vector<Fr>& c, const Fr& at) {
@@ -898,6 +951,13 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     *proof_out = out;
     *proof_len = pr->tr.proof.size();
     pr->stage = 2;
+    pr->mark(7);
+    return ZKFHE_OK;
+}
+
+int zkfhe_prover_round_ms(const zkfhe_prover* pr, double out[8]) {
+    if (!pr || !out) return ZKFHE_ERR_ARG;
+    memcpy(out, pr->round_ms, sizeof pr->round_ms);
     return ZKFHE_OK;
 }
 

@@ -56,13 +56,14 @@ TRANSCRIPT_BLAKE2B, TRANSCRIPT_POSEIDON = 0, 1
 class Prover:
     """One proof: phase0(witness) -> gamma; (caller runs the phase-1 chip calls); finish(witness) -> bytes."""
 
-    def __init__(self, pk, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B):
+    def __init__(self, pk, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B, ctx=None):
+        """`ctx`: the context (stream) this prover runs on; defaults to the key's own context."""
         self.pk = pk
-        self.ctx = pk.ctx
+        self.ctx = ctx or pk.ctx
         assert len(seed) == 32
         self._seed = bytearray(seed)
         h = ctypes.c_void_p()
-        self.ctx._check(self.ctx.lib.zkfhe_prove_begin(pk.h, _addr(self._seed), transcript, ctypes.byref(h)))
+        self.ctx._check(self.ctx.lib.zkfhe_prove_begin(self.ctx.h, pk.h, _addr(self._seed), transcript, ctypes.byref(h)))
         self.h = h
 
     def __del__(self):
@@ -72,6 +73,15 @@ class Prover:
         except Exception:
             pass
         self.h = None
+
+    ROUNDS = ("phase0_commit", "phase1_commit", "lookup_permute", "grand_products", "quotient", "evaluations",
+              "shplonk_quotient", "shplonk_opening")
+
+    def round_ms(self):
+        """Wall-clock of each round of the last proof (ms)."""
+        out = (ctypes.c_double * 8)()
+        self.ctx._check(self.ctx.lib.zkfhe_prover_round_ms(self.h, out))
+        return dict(zip(self.ROUNDS, (round(float(x), 3) for x in out)))
 
     def reset(self, seed):
         """Next proof with the same device buffers."""
