@@ -195,6 +195,19 @@ def test_srs_setup_on_gpu_matches_oracle(ctx):
     c2.close()
 
 
+def test_commit_columns_sharded_single_rank_equals_plain_msm(ctx):
+    """zk_fhe_b200.dist.commit_columns_sharded (the column-sharded commit phase) at world size 1."""
+    import torch
+    from zk_fhe_b200 import dist as zd
+    k, n, cols = 8, 256, 5
+    g, gl = toy_srs(k)
+    ctx.load_srs(k, g=g, g_lagrange=gl)
+    sc = random_fr_mont(np.random.default_rng(8), cols * n)
+    d = torch.from_numpy(sc.view(np.int64)).cuda()
+    got = zd.commit_columns_sharded(ctx, d, cols, basis=1).cpu().numpy().tobytes()
+    assert got == cbind.msm(sc, gl, n, cols).tobytes()
+
+
 def test_fr_convert_roundtrip(ctx):
     import torch
     vals = [0, 1, 2, field.R_MOD - 1, 1 << 200, 536870909]

@@ -32,9 +32,9 @@ def _nvcc():
 
 def _stamp():
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include"), os.path.join(HERE, "host")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h", ".py")):
+            if name.endswith((".cu", ".cuh", ".h", ".py", ".hpp", ".cpp")):
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode() + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -85,6 +85,12 @@ def build(force=False, verbose=False):
             f.write(ostamp)
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.run(cmd, check=True)
+    # the `bfv` example entrypoint (host C++ mirror of examples/bfv.rs over the C ABI)
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", os.path.join(HERE, "host", "bfv.cpp"), "-o",
+                    os.path.join(bindir, "bfv"), "-L" + LIBDIR, "-lzkfhe_b200", "-Wl,-rpath,$ORIGIN/../lib",
+                    "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
     with open(stamp_path, "w") as f:
         f.write(stamp)
     return LIB
