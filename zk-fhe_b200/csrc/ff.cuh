@@ -85,11 +85,16 @@ template <int F> __device__ __forceinline__ fe<F> from_mont(const fe<F>& a) {
     return mul(a, one_plain);
 }
 
-// a^e, e given as 8 plain LE limbs (not secret: variable time)
-template <int F> __device__ fe<F> pow_limbs(const fe<F>& a, const fe<F>& e) {
+// a^e, e given as 8 plain LE limbs (not secret: variable time).
+// The exponentiation helpers are cold (setup, one inversion per column / per row at most): they stay
+// out of line with rolled loops so that ptxas sees one copy of the product per helper, not hundreds
+// (fully inlined they made single kernels of 10^5 PTX lines and a 15-minute build).
+template <int F> __device__ __noinline__ fe<F> pow_limbs(const fe<F> a, const fe<F> e) {
     fe<F> acc = fe_one<F>();
     bool started = false;
+#pragma unroll 1
     for (int i = 7; i >= 0; i--) {
+#pragma unroll 1
         for (int bit = 31; bit >= 0; bit--) {
             if (started) acc = sqr(acc);
             if ((e.v[i] >> bit) & 1) {
@@ -101,11 +106,12 @@ template <int F> __device__ fe<F> pow_limbs(const fe<F>& a, const fe<F>& e) {
     return acc;
 }
 // Fermat inverse; inv(0) = 0
-template <int F> __device__ fe<F> inv(const fe<F>& a) { return pow_limbs(a, fconst<F>::mod_minus_2()); }
+template <int F> __device__ __forceinline__ fe<F> inv(const fe<F>& a) { return pow_limbs(a, fconst<F>::mod_minus_2()); }
 
-template <int F> __device__ fe<F> pow_u64(const fe<F>& a, unsigned long long e) {
+template <int F> __device__ __noinline__ fe<F> pow_u64(const fe<F> a, unsigned long long e) {
     fe<F> acc = fe_one<F>();
     fe<F> base = a;
+#pragma unroll 1
     while (e) {
         if (e & 1) acc = mul(acc, base);
         e >>= 1;

@@ -38,7 +38,9 @@ __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint3
     g1_affine p = affine_load(bases + i);
     affine_store(table + i, p);
     g1_xyzz q = xyzz_from_affine(p);
+#pragma unroll 1
     for (uint32_t w = 1; w < W; w++) {
+#pragma unroll 1
         for (uint32_t d = 0; d < c; d++) q = xyzz_dbl(q);
         g1_affine a = xyzz_to_affine(q);
         affine_store(table + (size_t)w * n + i, a);
@@ -310,13 +312,15 @@ __global__ void __launch_bounds__(THREADS) k_msm_final(uint32_t groups, uint32_t
 }
 
 // ---- test SRS (halo2 `ParamsKZG::setup` shape): g[i] = tau^i G, g_lagrange[i] = l_i(tau) G --------
-__device__ inline g1_affine g1_generator_mul(const fr_t& k_canon) {
+__device__ __noinline__ g1_affine g1_generator_mul(const fr_t k_canon) {
     g1_affine g;
     g.x = fe_one<FQ>();
     g.y = add(fe_one<FQ>(), fe_one<FQ>());      // G = (1, 2)
     g1_xyzz acc = xyzz_identity();
     bool started = false;
+#pragma unroll 1
     for (int i = 7; i >= 0; i--)
+#pragma unroll 1
         for (int bit = 31; bit >= 0; bit--) {
             if (started) acc = xyzz_dbl(acc);
             if ((k_canon.v[i] >> bit) & 1) { xyzz_madd(acc, g, false); started = true; }

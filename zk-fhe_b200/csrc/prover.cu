@@ -412,8 +412,9 @@ __global__ void k_lincomb(const fr_t* const* polys, const fr_t* coef, uint32_t m
 // SHPLONK quotient on the coset zeta*H: acc[row] += scale * (f[row] - r(c)) / Z(c), c = zeta * w^row.
 // r and Z are given by their coefficients (degree <= 3 and <= 4).
 struct SmallPoly { fr_t c[5]; uint32_t len; };
-__device__ __forceinline__ fr_t small_eval(const SmallPoly& p, const fr_t& x) {
+__device__ __noinline__ fr_t small_eval(const SmallPoly& p, const fr_t x) {   // cold: one copy, rolled
     fr_t acc = fe_zero<FR>();
+#pragma unroll 1
     for (int i = (int)p.len - 1; i >= 0; i--) acc = add(mul(acc, x), p.c[i]);
     return acc;
 }
