@@ -67,6 +67,12 @@ uint64_t zkfhe_launch_count(const zkfhe_ctx* ctx);
 /* On-device self test of the generated PTX field arithmetic against an independent plain-C
  * Montgomery product and algebraic identities; `mismatches` receives the failure count. */
 int zkfhe_selftest(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches);
+/* Arithmetic ceilings measured on this GPU, for the rooflines bench.py reports (the prove path is
+ * 256-bit modular integer work bound by the INT32 multiply pipe, not by HBM).  kind 0: Montgomery
+ * products with every SM full (`ops` = products executed in `ms`); kinds 1..5: a dependent chain of
+ * `iters` operations on one warp -- 1 XYZZ point addition, 2 mixed addition, 3 field product,
+ * 4 field inversion (binary Euclid), 5 field inversion (Fermat). */
+int zkfhe_microbench(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops);
 
 /* ---- stage (3): NTT over BN254 Fr --------------------------------------------------------
  * Replaces halo2 `best_fft` + EvaluationDomain scaling.  `batch` columns of n = 2^log_n

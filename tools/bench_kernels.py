@@ -38,7 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--k", type=int, default=13)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--what", default="msm,ntt")
+    ap.add_argument("--what", default="micro,msm,ntt")
     ap.add_argument("--full-cols", type=int, default=137)
     ap.add_argument("--small-cols", type=int, default=194)
     ap.add_argument("--ntt-cols", type=int, default=406)
@@ -68,6 +68,13 @@ def main():
             line += f"  | {64 * elems / ms / 1e6:7.1f} GB/s"
         print(line, flush=True)
 
+    if "micro" in args.what:
+        ms, ops = ctx.microbench(0, 2000)
+        print(f"montgomery products, full GPU   {ops / ms / 1e6:8.2f} G/s  ({ms:.3f} ms)", flush=True)
+        for kind, name, it in ((1, "xyzz add", 200), (2, "mixed add", 200), (3, "field product", 2000),
+                               (4, "inversion (binary Euclid)", 20), (5, "inversion (Fermat)", 20)):
+            ms, ops = ctx.microbench(kind, it)
+            print(f"one-warp chain: {name:28s} {1e3 * ms / ops:9.3f} us per op", flush=True)
     if "msm" in args.what:
         ctx.srs_setup(k, 0x5EED5EED)
         out = torch.zeros(64 * 512, dtype=torch.uint8, device=dev)

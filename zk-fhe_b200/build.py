@@ -19,7 +19,7 @@ SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-Wall", "-diag-suppress", "177",
+    "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "-diag-suppress", "177",
 ]
 
 

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "zkfhe_sync": (_c.c_int, [_c.c_void_p]),
     "zkfhe_launch_count": (_c.c_uint64, [_c.c_void_p]),
     "zkfhe_selftest": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_uint32)]),
+    "zkfhe_microbench": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint64)]),
     "zkfhe_ntt_fr": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
     "zkfhe_ntt_fr_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
     "zkfhe_coeff_to_extended_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _u8p, _c.c_uint32, _c.c_uint32]),
@@ -229,6 +230,13 @@ class Context:
         bad = ctypes.c_uint32(0)
         self._check(self.lib.zkfhe_selftest(self.h, n_cases, seed, ctypes.byref(bad)))
         return bad.value
+
+    def microbench(self, kind, iters):
+        """(ms, ops) of an arithmetic micro-benchmark: kind 0 Montgomery-product throughput on a full
+        GPU; 1..5 one-warp dependent chains (XYZZ add, mixed add, product, inversion, Fermat inversion)."""
+        ms, ops = ctypes.c_float(), ctypes.c_uint64()
+        self._check(self.lib.zkfhe_microbench(self.h, kind, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        return float(ms.value), int(ops.value)
 
     # -- stage (3) ----------------------------------------------------------
     def ntt_fr(self, data, log_n, batch, inverse=False, coset=False):

@@ -54,8 +54,11 @@ __global__ void k_selftest(uint32_t n_cases, uint64_t seed, uint32_t* mismatches
     if (i < 64) {   // inversions and curve identities on a few threads only
         fr_t a = random_fe<FR>(s);
         if (!is_zero(a) && !eq(mul(a, inv(a)), fe_one<FR>())) bad++;
+        if (!eq(inv(a), inv_fermat(a))) bad++;
         fq_t q = random_fe<FQ>(s);
         if (!is_zero(q) && !eq(mul(q, inv(q)), fe_one<FQ>())) bad++;
+        if (!eq(inv(q), inv_fermat(q))) bad++;
+        if (!is_zero(inv(fe_zero<FQ>())) || !eq(inv(fe_one<FQ>()), fe_one<FQ>())) bad++;
         // G = (1, 2) in Montgomery form; check 2G + G == 3G via two routes and the curve equation
         g1_affine g;
         g.x = fe_one<FQ>();
@@ -90,6 +93,69 @@ int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mism
     ZK_CUDA(ctx, cudaMemcpyAsync(mismatches, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ZK_CUDA(ctx, cudaFree(d_bad));
+    return ZKFHE_OK;
+}
+
+// ---- micro-benchmarks: the arithmetic ceilings the kernel rooflines are quoted against -----------
+// kind 0: Montgomery products/s with every SM full (two independent chains per thread) -- the
+//         IMAD-pipe peak that bounds MSM and NTT long before HBM does;
+// kind 1..5: latency of a dependent chain on ONE warp: 1 XYZZ add, 2 mixed add, 3 field product,
+//         4 inversion (binary Euclid), 5 inversion (Fermat).
+__global__ void __launch_bounds__(256) k_bench_mul(fq_t* out, uint32_t iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    fq_t a = fe_one<FQ>(), b = fconst<FQ>::r2(), c = fconst<FQ>::r3(), d = fconst<FQ>::r2();
+    a.v[0] += t; c.v[1] ^= t;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) { a = mul(a, b); c = mul(c, d); }
+    fe_store(out + t, add(a, c));
+}
+__global__ void __launch_bounds__(32) k_bench_chain(int kind, uint32_t iters, g1_xyzz* out) {
+    g1_affine g;
+    g.x = fe_one<FQ>();
+    g.y = add(fe_one<FQ>(), fe_one<FQ>());
+    g1_xyzz p = xyzz_from_affine(g), acc = xyzz_dbl_affine(g);
+    acc.x.v[0] += 0;
+    if (kind == 1) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) xyzz_add(acc, p);
+    } else if (kind == 2) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) xyzz_madd(acc, g, false);
+    } else if (kind == 3) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) acc.x = mul(acc.x, acc.y);
+    } else if (kind == 4) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) acc.x = add(inv(acc.x), acc.y);
+    } else {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) acc.x = add(inv_fermat(acc.x), acc.y);
+    }
+    if (threadIdx.x == 0) xyzz_store(out, acc);
+}
+
+int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops) {
+    if (kind < 0 || kind > 5 || !iters) return fail(ctx, ZKFHE_ERR_ARG, "microbench: kind in [0,5], iters > 0");
+    cudaDeviceProp prop;
+    ZK_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const uint32_t blocks = (uint32_t)prop.multiProcessorCount * 8, threads = 256;
+    void* buf;
+    ZK_TRY(ws_get(ctx, "microbench", (size_t)blocks * threads * sizeof(fq_t) + sizeof(g1_xyzz), &buf));
+    cudaEvent_t e0, e1;
+    ZK_CUDA(ctx, cudaEventCreate(&e0));
+    ZK_CUDA(ctx, cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {          // first pass warms up; the second is the one reported
+        ZK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) k_bench_mul<<<blocks, threads, 0, ctx->stream>>>((fq_t*)buf, iters);
+        else k_bench_chain<<<1, 32, 0, ctx->stream>>>(kind, iters, (g1_xyzz*)buf);
+        ZK_CHECK_LAUNCH(ctx);
+        ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        ZK_CUDA(ctx, cudaEventSynchronize(e1));
+    }
+    ZK_CUDA(ctx, cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops = kind == 0 ? (uint64_t)blocks * threads * iters * 2 : (uint64_t)iters;
     return ZKFHE_OK;
 }
 
@@ -189,6 +255,12 @@ int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, u
     if (spans) *spans = cnt;
     if (units) *units = un;
     return ZKFHE_OK;
+}
+
+int zkfhe_microbench(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops) {
+    if (!ctx || !ms || !ops) return ZKFHE_ERR_ARG;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return microbench_run(ctx, kind, iters, ms, ops);
 }
 
 int zkfhe_selftest(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches) {

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "ff_ptx_gen.cuh"
+#include "inv_bin.cuh"
 
 namespace zkfhe {
 
@@ -28,6 +29,7 @@ template <> struct fconst<FR> {
     static __device__ __forceinline__ fe<FR> mod() { return fe<FR>{ZKFHE_FR_MOD}; }
     static __device__ __forceinline__ fe<FR> one() { return fe<FR>{ZKFHE_FR_ONE}; }
     static __device__ __forceinline__ fe<FR> r2() { return fe<FR>{ZKFHE_FR_R2}; }
+    static __device__ __forceinline__ fe<FR> r3() { return fe<FR>{ZKFHE_FR_R3}; }
     static __device__ __forceinline__ fe<FR> mod_minus_2() { return fe<FR>{ZKFHE_FR_MOD_MINUS_2}; }
     static constexpr uint32_t inv32 = ZKFHE_FR_INV32;
 };
@@ -35,6 +37,7 @@ template <> struct fconst<FQ> {
     static __device__ __forceinline__ fe<FQ> mod() { return fe<FQ>{ZKFHE_FQ_MOD}; }
     static __device__ __forceinline__ fe<FQ> one() { return fe<FQ>{ZKFHE_FQ_ONE}; }
     static __device__ __forceinline__ fe<FQ> r2() { return fe<FQ>{ZKFHE_FQ_R2}; }
+    static __device__ __forceinline__ fe<FQ> r3() { return fe<FQ>{ZKFHE_FQ_R3}; }
     static __device__ __forceinline__ fe<FQ> mod_minus_2() { return fe<FQ>{ZKFHE_FQ_MOD_MINUS_2}; }
     static constexpr uint32_t inv32 = ZKFHE_FQ_INV32;
 };
@@ -105,8 +108,16 @@ template <int F> __device__ __noinline__ fe<F> pow_limbs(const fe<F> a, const fe
     }
     return acc;
 }
-// Fermat inverse; inv(0) = 0
-template <int F> __device__ __forceinline__ fe<F> inv(const fe<F>& a) { return pow_limbs(a, fconst<F>::mod_minus_2()); }
+// Fermat inverse; inv(0) = 0.  Kept as the independent cross-check of `inv` in the device self test.
+template <int F> __device__ __forceinline__ fe<F> inv_fermat(const fe<F>& a) { return pow_limbs(a, fconst<F>::mod_minus_2()); }
+// Inverse of a Montgomery-form element: binary extended Euclid on the raw limbs gives (aR)^-1,
+// one product with R^3 brings it back to a^-1 R.  inv(0) = 0.
+template <int F> __device__ __noinline__ fe<F> inv(const fe<F> a) {
+    fe<F> t;
+    const fe<F> p = fconst<F>::mod();
+    u256_inv_odd(t.v, a.v, p.v);
+    return mul(t, fconst<F>::r3());
+}
 
 template <int F> __device__ __noinline__ fe<F> pow_u64(const fe<F> a, unsigned long long e) {
     fe<F> acc = fe_one<F>();

@@ -49,22 +49,17 @@ __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint3
 }
 
 // ---- digit recoding -----------------------------------------------------------------------
-// bits [off, off+c) of a 256-bit little-endian integer, c <= 16
-__device__ __forceinline__ uint32_t get_bits(const fr_t& s, uint32_t off, uint32_t c) {
-    uint32_t limb = off >> 5, sh = off & 31;
-    uint64_t two = s.v[limb];
-    if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
-    return (uint32_t)(two >> sh) & ((1u << c) - 1);
-}
-
-// Calls f(w, bucket_index, negative) for every non-zero signed digit of the scalar.
+// Calls f(w, bucket_index, negative) for every non-zero signed c-bit digit of the scalar
+// (W = ceil(255/c) windows, c <= 16).  The limbs stream through a 64-bit shift register with
+// compile-time limb indices: indexing the limb array by a run-time window offset made ptxas
+// select limbs with compare chains, ~5x the instructions of the whole sort kernel.
 template <class Fn>
 __device__ __forceinline__ void for_each_digit(const fr_t& s_canon, uint32_t c, uint32_t W, Fn f) {
-    uint32_t carry = 0;
-    const uint32_t halfw = 1u << (c - 1);
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t off = w * c;
-        uint32_t d = (off < 256 ? get_bits(s_canon, off, (off + c <= 256) ? c : 256 - off) : 0) + carry;
+    const uint32_t mask = (1u << c) - 1, halfw = 1u << (c - 1);
+    uint64_t buf = 0;
+    uint32_t nbits = 0, w = 0, carry = 0;
+    auto emit = [&](uint32_t raw) {
+        uint32_t d = raw + carry;
         if (d > halfw) {
             carry = 1;
             uint32_t mag = (1u << c) - d;           // digit = d - 2^c < 0
@@ -73,7 +68,19 @@ __device__ __forceinline__ void for_each_digit(const fr_t& s_canon, uint32_t c, 
             carry = 0;
             if (d) f(w, d - 1, false);
         }
+        w++;
+    };
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        buf |= (uint64_t)s_canon.v[l] << nbits;
+        nbits += 32;
+        while (nbits >= c && w < W) {
+            emit((uint32_t)buf & mask);
+            buf >>= c;
+            nbits -= c;
+        }
     }
+    if (w < W) emit((uint32_t)buf & mask);          // the last, short window
 }
 
 // One CTA per column: histogram -> exclusive scans -> scatter (counting sort by bucket).
@@ -267,48 +274,61 @@ __global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uin
     xyzz_store(o + 1, acc);
 }
 
-// Reduction, level 2: one CTA per column, one thread per group.
-//   total = sum_g A_g + fold * sum_g g * S_g,   sum_g g * S_g = sum_{g>=1} U_g,  U_g = sum_{h>=g} S_h
-// U is a suffix scan in shared memory (log2(groups) steps), the two sums are tree reductions.
-extern __shared__ uint4 msm_final_smem[];
-template <uint32_t THREADS>
-__global__ void __launch_bounds__(THREADS) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
-                                                       g1_affine* out) {
-    g1_xyzz* U = reinterpret_cast<g1_xyzz*>(msm_final_smem);     // [groups]
-    g1_xyzz* A = U + groups;                                      // [groups]
-    const uint32_t col = blockIdx.x, t = threadIdx.x;
-    const g1_xyzz* in = group_in + ((size_t)col * groups + t) * 2;
-    g1_xyzz u = xyzz_load(in);
-    xyzz_store(&U[t], u);
-    xyzz_store(&A[t], xyzz_load(in + 1));
-    __syncthreads();
-    for (uint32_t d = 1; d < groups; d <<= 1) {                   // suffix scan (Hillis-Steele)
-        bool act = t + d < groups;
-        g1_xyzz v;
-        if (act) v = xyzz_load(&U[t + d]);
-        __syncthreads();
-        if (act) { xyzz_add_ni(u, v); xyzz_store(&U[t], u); }
-        __syncthreads();
+// Reduction, level 2: ONE WARP per column, lane l owning `per` consecutive groups.
+//   total = sum_g A_g + fold * sum_g g * S_g
+// Inside a lane (g0 = l * per): S_l = sum S_g, W_l = sum (g - g0) S_g (running sums), A_l = sum A_g.
+// Across lanes: U_l = sum_{m >= l} S_m by a shuffle suffix scan, so sum_l l * S_l = sum_{l >= 1} U_l;
+// every lane then forms V_l = A_l + fold * (W_l + per * [l >= 1] U_l) with doublings (fold and per
+// are powers of two) and one shuffle tree adds the 32 V_l.  No shared memory, no barriers, ~1/3 of
+// the point additions of a block-wide Hillis-Steele scan, and a column costs one warp instead of a
+// whole SM; the single inversion per column is binary Euclid (inv_bin.cuh), off the IMAD pipe.
+__device__ __forceinline__ g1_xyzz xyzz_shfl_down(const g1_xyzz& p, uint32_t d) {
+    g1_xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
     }
-    if (t == 0) xyzz_store(&U[0], xyzz_identity());               // the g = 0 term has weight 0
-    __syncthreads();
-    // two tree reductions side by side: threads [0, stride) fold U, threads [stride, 2*stride) fold A
-    for (uint32_t stride = groups >> 1; stride > 0; stride >>= 1) {
-        if (t < 2 * stride) {          // within a level, X[i] is read and written by thread i only
-            g1_xyzz* X = t < stride ? U : A;
-            const uint32_t i = t < stride ? t : t - stride;
-            g1_xyzz a = xyzz_load(&X[i]);
-            xyzz_add_ni(a, xyzz_load(&X[i + stride]));
-            xyzz_store(&X[i], a);
+    return r;
+}
+__device__ __noinline__ g1_xyzz xyzz_dbl_ni(const g1_xyzz p) { return xyzz_dbl(p); }
+
+__global__ void __launch_bounds__(32) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
+                                                  g1_affine* out) {
+    const uint32_t col = blockIdx.x, lane = threadIdx.x;
+    uint32_t log_per = 0;
+    while ((32u << log_per) < groups) log_per++;                  // groups is a power of two
+    const uint32_t per = 1u << log_per, g0 = lane << log_per;
+    const g1_xyzz* in = group_in + (size_t)col * groups * 2;
+    g1_xyzz S = xyzz_identity(), Wt = xyzz_identity(), A = xyzz_identity();
+    if (g0 < groups) {
+#pragma unroll 1
+        for (uint32_t g = g0 + per; g-- > g0;) {
+            xyzz_add_ni(S, xyzz_load(in + 2 * (size_t)g));
+            if (g > g0) xyzz_add_ni(Wt, S);
+            xyzz_add_ni(A, xyzz_load(in + 2 * (size_t)g + 1));
         }
-        __syncthreads();
     }
-    if (t == 0) {
-        g1_xyzz w = xyzz_load(&U[0]);
-        for (uint32_t i = 0; i < log_fold; i++) w = xyzz_dbl(w);
-        xyzz_add_ni(w, xyzz_load(&A[0]));
-        affine_store(out + col, xyzz_to_affine(w));
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {                       // inclusive suffix scan of S over the lanes
+        g1_xyzz v = xyzz_shfl_down(S, d);
+        if (lane + d < 32) xyzz_add_ni(S, v);
     }
+    g1_xyzz V = lane ? S : xyzz_identity();
+#pragma unroll 1
+    for (uint32_t i = 0; i < log_per; i++) V = xyzz_dbl_ni(V);
+    xyzz_add_ni(V, Wt);
+#pragma unroll 1
+    for (uint32_t i = 0; i < log_fold; i++) V = xyzz_dbl_ni(V);
+    xyzz_add_ni(V, A);
+#pragma unroll 1
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        g1_xyzz v = xyzz_shfl_down(V, d);
+        if (lane < d) xyzz_add_ni(V, v);
+    }
+    if (lane == 0) affine_store(out + col, xyzz_to_affine(V));
 }
 
 // ---- test SRS (halo2 `ParamsKZG::setup` shape): g[i] = tau^i G, g_lagrange[i] = l_i(tau) G --------
@@ -427,20 +447,17 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     const uint64_t max_segs2 = NB + (max_thr + SUP - 1) / SUP + 1;      // level-2 slots: rank[b] + super-slice
     g1_xyzz* partial2;
     ZK_TRY(ws_get(ctx, "msm_partial2", (size_t)chunk * max_segs2 * sizeof(g1_xyzz), (void**)&partial2));
-    // reduction shape: groups of 2^log_fold buckets, one thread per group in the final CTA
-    // (a few columns: narrow groups and a 1024-thread final CTA keep the dependent chain short;
-    //  many columns: wide groups, the kernels are throughput-bound anyway)
-    uint32_t log_fold = batch < 32 ? 3 : 4;
+    // reduction shape: groups of 2^log_fold buckets; the final warp owns groups/32 groups per lane.
+    // 16 buckets per fold thread and <= 512 groups balance the two dependent chains (2*fold and
+    // 3*groups/32 point additions).
+    uint32_t log_fold = 4;
     while (log_fold && (NB >> log_fold) == 0) log_fold--;
-    while ((NB >> log_fold) > (batch < 32 ? 512u : 256u)) log_fold++;
+    while ((NB >> log_fold) > 512u) log_fold++;
     const uint32_t groups = NB >> log_fold;
     g1_xyzz* grp;
     ZK_TRY(ws_get(ctx, "msm_groups", (size_t)chunk * groups * 2 * sizeof(g1_xyzz), (void**)&grp));
-    const size_t fsmem = (size_t)groups * 2 * sizeof(g1_xyzz);
     // function attributes are process-wide: always raise them to the fixed maximum any call can need,
     // never to this call's size (several contexts may be launching from different host threads)
-    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * (int)sizeof(g1_xyzz)));
-    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 2 * (int)sizeof(g1_xyzz)));
     size_t smem = (size_t)NB * 4;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     timed_call_start(ctx);
@@ -465,8 +482,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
-        if (groups <= 256) k_msm_final<256><<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
-        else k_msm_final<512><<<nb, groups, fsmem, ctx->stream>>>(groups, log_fold, grp, d_out + done);
+        k_msm_final<<<nb, 32, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
     }
