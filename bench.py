@@ -63,6 +63,16 @@ def synth_columns(rng, count):
     return cols.reshape(count * N_ROWS, 4)
 
 
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    command (profiles/r01_traffic.json, written by tools/ncu_traffic.py); {} if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+TRAFFIC = _traffic()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -359,7 +369,12 @@ def main():
     acc_ms, acc_spans, acc_pairs = ctx.timing(0)
     ntt_ms, ntt_spans, ntt_elems = ctx.timing(1)
     red_ms = ctx.timing(2)[0] + ctx.timing(3)[0] + ctx.timing(4)[0]
+    msm_adds = ctx.timing(5)[2]                 # mixed point additions issued by k_msm_accumulate (10 field products each)
+    ntt_products = ctx.timing(6)[2]
     proof_len = [streams[0].proof_len]
+    # the arithmetic ceiling of this GPU, measured live: Montgomery products/s with every SM full
+    mb_ms, mb_ops = ctx.microbench(0, 2000)
+    peak_products = mb_ops / (mb_ms * 1e-3)
 
     if rank == 0:
         peak, peak_kind = peaks()
@@ -379,7 +394,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": peak,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": TRAFFIC.get("k_msm_accumulate_dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": MSM_BYTES_PER_PAIR * acc_pairs / max(acc_spans, 1),
                          "kernel_ms_per_launch": acc_ms / max(acc_spans, 1), "launches_per_proof": acc_spans / lat_steps,
                          "share_of_single_stream_proof": acc_ms / (lat_ms * lat_steps),
@@ -388,7 +403,9 @@ def main():
                                  "see DESIGN.md for the IMAD-pipe roofline"},
             "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ntt_ach, "peak": peak, "unit": "GB/s",
                              "frac": ntt_ach / peak, "share_of_single_stream_proof": ntt_ms / (lat_ms * lat_steps),
-                             "kernel_ms_per_proof": ntt_ms / lat_steps},
+                             "kernel_ms_per_proof": ntt_ms / lat_steps,
+                             "imad": {"unit": "G Montgomery products/s", "achieved": ntt_products / (ntt_ms * 1e-3) / 1e9,
+                                      "peak": peak_products / 1e9, "frac": ntt_products / (ntt_ms * 1e-3) / peak_products}},
             "single_stream": {"prove_latency_ms": lat_ms, "msm_accumulate_ms": acc_ms / lat_steps,
                               "msm_sort_reduce_ms": red_ms / lat_steps, "ntt_ms": ntt_ms / lat_steps,
                               "other_ms": lat_ms - (acc_ms + ntt_ms + red_ms) / lat_steps},

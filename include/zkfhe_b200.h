@@ -276,7 +276,10 @@ float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx);
 /* Accumulated device time per kernel category since zkfhe_timing_reset (CUDA events recorded on
  * the context's stream around every launch of that category, so whole-proof shares can be read
  * without a profiler).  category 0: MSM bucket accumulation (units = scalar/point pairs),
- * 1: NTT passes (units = field elements transformed), 2: MSM sort + bucket reduction. */
+ * 1: NTT passes (units = field elements transformed), 2: MSM counting sort, 3: MSM bucket folding,
+ * 4: MSM final reduction, 5: no time -- units = point additions issued by the accumulate kernel
+ * (non-zero signed digits), the numerator of the IMAD-pipe roofline; 6: no time -- units = field
+ * products issued by the NTT passes (butterflies + 4-step twiddles + coset / n^-1 factors). */
 int zkfhe_timing_reset(zkfhe_ctx* ctx);
 int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, uint64_t* units);
 

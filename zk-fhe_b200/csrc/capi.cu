@@ -234,11 +234,32 @@ int zkfhe_timing_reset(zkfhe_ctx* ctx) {
     if (!ctx) return ZKFHE_ERR_ARG;
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ev_used = ctx->call_mark = 0;
+    ctx->ntt_products = 0;
+    auto it = ctx->ws.find("msm_refs");
+    if (it != ctx->ws.end()) ZK_CUDA(ctx, cudaMemset(it->second.p, 0, 8));
     return ZKFHE_OK;
 }
 
 int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, uint64_t* units) {
     if (!ctx || category < 0 || category >= ZK_CAT_COUNT) return ZKFHE_ERR_ARG;
+    if (category == ZK_CAT_MSM_REFS) {
+        unsigned long long v = 0;
+        auto it = ctx->ws.find("msm_refs");
+        if (it != ctx->ws.end()) {
+            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ZK_CUDA(ctx, cudaMemcpy(&v, it->second.p, 8, cudaMemcpyDeviceToHost));
+        }
+        if (ms) *ms = 0.f;
+        if (spans) *spans = 0;
+        if (units) *units = v;
+        return ZKFHE_OK;
+    }
+    if (category == ZK_CAT_NTT_PRODUCTS) {
+        if (ms) *ms = 0.f;
+        if (spans) *spans = 0;
+        if (units) *units = ctx->ntt_products;
+        return ZKFHE_OK;
+    }
     float total = 0.f;
     uint32_t cnt = 0;
     uint64_t un = 0;

@@ -51,8 +51,11 @@ struct zkfhe_ctx {
     struct SpanInfo { int cat; uint64_t units; };
     std::vector<SpanInfo> ev_info;
     size_t ev_used = 0, call_mark = 0;
+    uint64_t ntt_products = 0;                   // butterflies + twiddle / coset / scaling products since timing_reset
 };
-enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4, ZK_CAT_COUNT = 5 };
+enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4,
+       ZK_CAT_MSM_REFS = 5 /* no time: units = point additions issued by the accumulate kernel */, 
+       ZK_CAT_NTT_PRODUCTS = 6 /* no time: units = field products issued by the NTT passes */, ZK_CAT_COUNT = 7 };
 
 namespace zkfhe {
 

@@ -296,8 +296,10 @@ __device__ __forceinline__ g1_xyzz xyzz_shfl_down(const g1_xyzz& p, uint32_t d) 
 __device__ __noinline__ g1_xyzz xyzz_dbl_ni(const g1_xyzz p) { return xyzz_dbl(p); }
 
 __global__ void __launch_bounds__(32) k_msm_final(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
-                                                  g1_affine* out) {
+                                                  g1_affine* out, const uint32_t* __restrict__ bucket_off, uint32_t NB,
+                                                  unsigned long long* refs_total) {
     const uint32_t col = blockIdx.x, lane = threadIdx.x;
+    if (lane == 0) atomicAdd(refs_total, (unsigned long long)bucket_off[(size_t)col * (NB + 1) + NB]);
     uint32_t log_per = 0;
     while ((32u << log_per) < groups) log_per++;                  // groups is a power of two
     const uint32_t per = 1u << log_per, g0 = lane << log_per;
@@ -459,6 +461,12 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     // function attributes are process-wide: always raise them to the fixed maximum any call can need,
     // never to this call's size (several contexts may be launching from different host threads)
     size_t smem = (size_t)NB * 4;
+    unsigned long long* refs;       // running count of point additions (zkfhe_timing_get category 5)
+    {
+        const bool fresh = ctx->ws.find("msm_refs") == ctx->ws.end();
+        ZK_TRY(ws_get(ctx, "msm_refs", 8, (void**)&refs));
+        if (fresh) ZK_CUDA(ctx, cudaMemsetAsync(refs, 0, 8, ctx->stream));
+    }
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
@@ -482,7 +490,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
-        k_msm_final<<<nb, 32, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done);
+        k_msm_final<<<nb, 32, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done, boff, NB, refs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
     }

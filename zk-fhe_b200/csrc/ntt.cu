@@ -204,6 +204,11 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         ZK_TRY(launch_pass(ctx, p, 1u << (log_ra - p.log_l), batch));
     }
     ZK_TRY(timed_end(ctx));
+    {   // products issued: one per butterfly, plus the per-element 4-step twiddle, coset and n^-1 factors (x3 = thirds)
+        const uint64_t elems = (uint64_t)batch << log_n;
+        uint64_t thirds = (log_n > 11 ? 3 : 0) + (coset ? 2 : 0) + (inverse ? 3 : 0);
+        ctx->ntt_products += elems / 2 * log_n + elems * thirds / 3;
+    }
     return ZKFHE_OK;
 }
 
