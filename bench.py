@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transcript", type=int, default=0, help="0 BLAKE2b (default), 1 Poseidon")
-    ap.add_argument("--streams", type=int, default=4, help="proofs in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--streams", type=int, default=8, help="proofs in flight per GPU (one CUDA stream + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -399,8 +399,17 @@ def main():
                          "kernel_ms_per_launch": acc_ms / max(acc_spans, 1), "launches_per_proof": acc_spans / lat_steps,
                          "share_of_single_stream_proof": acc_ms / (lat_ms * lat_steps),
                          "measured": "one proof stream alone, CUDA events around every launch on its stream",
-                         "note": "256-bit modular arithmetic: INT32 IMAD-bound long before HBM (SURVEY §8d); "
-                                 "see DESIGN.md for the IMAD-pipe roofline"},
+                         "traffic_source": TRAFFIC.get("source"),
+                         "imad": {"bound": "int32 multiply pipe (fmaheavy)", "unit": "G Montgomery products/s",
+                                  "achieved": 10 * msm_adds / (acc_ms * 1e-3) / 1e9, "peak": peak_products / 1e9,
+                                  "frac": 10 * msm_adds / (acc_ms * 1e-3) / peak_products,
+                                  "point_additions_per_proof": msm_adds / lat_steps,
+                                  "peak_source": "zkfhe_microbench kind 0, measured in this run (two independent product "
+                                                 "chains per thread, 8 CTAs x 256 threads per SM)"},
+                         "note": "256-bit modular arithmetic: every kernel of the proof is bound by the INT32 multiply pipe "
+                                 "(ncu sm__pipe_fmaheavy_cycles_active 87% for this kernel, profiles/), not by HBM; the "
+                                 "hbm fraction is reported because the metric names it, the imad fraction is the one that "
+                                 "says how close the kernel is to the chip's ceiling"},
             "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ntt_ach, "peak": peak, "unit": "GB/s",
                              "frac": ntt_ach / peak, "share_of_single_stream_proof": ntt_ms / (lat_ms * lat_steps),
                              "kernel_ms_per_proof": ntt_ms / lat_steps,

@@ -108,6 +108,12 @@ int zkfhe_fr_convert_dev(zkfhe_ctx* ctx, uint8_t* d_data, uint64_t count, int to
 /* out[b] = sum_i scalars[b][i] * basis[i], b < batch; scalars are batch x 2^k Fr. */
 int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int basis, uint8_t* h_out_affine);
 int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, uint8_t* d_out_affine);
+/* Same, with a hint: `small_values` != 0 says the columns hold witness cells / lookup inputs (values
+ * far below the field size, a few full-size ones allowed).  The result is identical; the MSM then
+ * buckets with a narrower window whose reduction is 8x cheaper -- what `create_proof` pays for on
+ * the 269 advice / permuted-lookup columns of a config-1 proof. */
+int zkfhe_msm_g1_dev_ex(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, int small_values,
+                        uint8_t* d_out_affine);
 
 /* ---- stage (1a): off-circuit polynomial arithmetic ----------------------------------------
  * Device-resident mirror of `zk_fhe::poly::Poly` (src/poly.rs:9-13): `len` plain integer

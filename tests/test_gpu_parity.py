@@ -180,6 +180,32 @@ def test_msm_k13_witness_like_columns_match_oracle(ctx):
     assert ps == curve.g1_add(_pt(got[0]), _pt(got[1]))
 
 
+def test_msm_small_value_hint_gives_identical_points(ctx):
+    """zkfhe_msm_g1_dev_ex(small_values=1) (narrow-window table) == the plain MSM == the oracle, on
+    witness-like, full-size, all-zero and single-hot-bucket columns."""
+    import torch
+    k, n = 13, 1 << 13
+    _, gl = toy_srs(k)
+    ctx.load_srs(k, g=None, g_lagrange=gl)
+    rng = np.random.default_rng(5)
+    pyr = random.Random(5)
+    cols = [random_fr_mont(rng, n),
+            fr_to_mont_array([pyr.randrange(536870909) if i % 5 else (field.R_MOD - 1 - i) for i in range(n)]),
+            fr_to_mont_array([pyr.randrange(4096) for _ in range(n)]),
+            fr_to_mont_array([0] * n),
+            fr_to_mont_array([7] * n)]
+    scal = np.ascontiguousarray(np.concatenate(cols))
+    want = cbind.msm(scal, gl, n, len(cols))
+    d = torch.from_numpy(scal.view(np.int64).reshape(-1)).cuda()
+    out = torch.zeros(len(cols) * 8, dtype=torch.int64, device="cuda")
+    for small in (True, False):
+        out.zero_()
+        ctx.msm_g1_dev(d.data_ptr(), len(cols), 1, out.data_ptr(), small_values=small)
+        ctx.sync()
+        got = out.cpu().numpy().view(np.uint64).reshape(len(cols), 8)
+        assert np.array_equal(got, want), f"small_values={small}"
+
+
 def test_srs_setup_on_gpu_matches_oracle(ctx):
     """zkfhe_srs_setup (ParamsKZG::setup shape) vs the oracle's g[i] = tau^i G, g_lagrange[i] = l_i(tau) G."""
     import zk_fhe_b200

@@ -78,15 +78,17 @@ def main():
     if "msm" in args.what:
         ctx.srs_setup(k, 0x5EED5EED)
         out = torch.zeros(64 * 512, dtype=torch.uint8, device=dev)
-        for tag, cols, gen in (("msm full-size", args.full_cols, full_size), ("msm witness-like", args.small_cols, witness_like),
-                               ("msm full-size x3", 3, full_size), ("msm full-size x1", 1, full_size)):
+        for tag, cols, gen, small in (("msm full-size", args.full_cols, full_size, False),
+                                      ("msm witness-like", args.small_cols, witness_like, False),
+                                      ("msm witness-like +hint", args.small_cols, witness_like, True),
+                                      ("msm full-size x3", 3, full_size, False), ("msm full-size x1", 1, full_size, False)):
             d = upload(gen(rng, cols, n))
             ctx.fr_convert_dev(d.data_ptr(), cols * n, True)
-            ctx.msm_g1_dev(d.data_ptr(), cols, 1, out.data_ptr())      # warm-up (workspace allocation)
+            ctx.msm_g1_dev(d.data_ptr(), cols, 1, out.data_ptr(), small_values=small)      # warm-up (workspace allocation)
             ctx.sync()
             ctx.timing_reset()
             for _ in range(args.iters):
-                ctx.msm_g1_dev(d.data_ptr(), cols, 1, out.data_ptr())
+                ctx.msm_g1_dev(d.data_ptr(), cols, 1, out.data_ptr(), small_values=small)
             report(f"{tag} [{cols} x 2^{k}]", pairs=cols * n)
     if "ntt" in args.what:
         cols = args.ntt_cols

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "zkfhe_fr_convert_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint64, _c.c_int]),
     "zkfhe_msm_g1": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
     "zkfhe_msm_g1_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _u8p]),
+    "zkfhe_msm_g1_dev_ex": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_int, _c.c_int, _u8p]),
     "zkfhe_last_kernel_ms": (_c.c_float, [_c.c_void_p]),
     "zkfhe_timing_reset": (_c.c_int, [_c.c_void_p]),
     "zkfhe_timing_get": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint32),
@@ -277,5 +278,8 @@ class Context:
         self._check(self.lib.zkfhe_msm_g1(self.h, _addr(scalars), batch, basis, _addr(out)))
         return bytes(out)
 
-    def msm_g1_dev(self, d_scalars, batch, basis, d_out):
-        self._check(self.lib.zkfhe_msm_g1_dev(self.h, d_scalars, batch, basis, d_out))
+    def msm_g1_dev(self, d_scalars, batch, basis, d_out, small_values=False):
+        if small_values:
+            self._check(self.lib.zkfhe_msm_g1_dev_ex(self.h, d_scalars, batch, basis, 1, d_out))
+        else:
+            self._check(self.lib.zkfhe_msm_g1_dev(self.h, d_scalars, batch, basis, d_out))

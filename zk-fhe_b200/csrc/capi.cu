@@ -189,8 +189,8 @@ void zkfhe_destroy(zkfhe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (auto& kv : ctx->domains) { cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); }
-    for (auto& b : ctx->basis) if (b.table && !b.shared) cudaFree(b.table);
+    for (auto& kv : ctx->domains) { cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); cudaFree(kv.second.tw_inv_s); }
+    for (auto& b : ctx->basis) if (b.table && !b.shared) { cudaFree(b.table); if (b.table_s) cudaFree(b.table_s); }
     for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -369,7 +369,10 @@ int zkfhe_share_srs(zkfhe_ctx* dst, const zkfhe_ctx* src) {
     if (dst->device != src->device) return fail(dst, ZKFHE_ERR_ARG, "share_srs: contexts are on different devices");
     if (src->srs_k == 0) return fail(dst, ZKFHE_ERR_STATE, "share_srs: the source context has no SRS");
     for (int i = 0; i < 2; i++) {
-        if (dst->basis[i].table && !dst->basis[i].shared) cudaFree(dst->basis[i].table);
+        if (dst->basis[i].table && !dst->basis[i].shared) {
+            cudaFree(dst->basis[i].table);
+            if (dst->basis[i].table_s) cudaFree(dst->basis[i].table_s);
+        }
         dst->basis[i] = src->basis[i];
         dst->basis[i].shared = true;
     }
@@ -389,6 +392,15 @@ int zkfhe_msm_g1_dev(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, i
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     return msm_run(ctx, reinterpret_cast<const fr_t*>(d_scalars), 1ull << ctx->srs_k, ctx->srs_k, batch, basis,
                    reinterpret_cast<g1_affine*>(d_out_affine));
+}
+
+int zkfhe_msm_g1_dev_ex(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch, int basis, int small_values,
+                        uint8_t* d_out_affine) {
+    if (!ctx || !d_scalars || !d_out_affine) return fail(ctx, ZKFHE_ERR_ARG, "msm: null pointer");
+    if (ctx->srs_k == 0) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return msm_run(ctx, reinterpret_cast<const fr_t*>(d_scalars), 1ull << ctx->srs_k, ctx->srs_k, batch, basis,
+                   reinterpret_cast<g1_affine*>(d_out_affine), small_values);
 }
 
 int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int basis, uint8_t* h_out_affine) {

@@ -23,6 +23,11 @@ struct DevBuf {
 struct MsmBasis {
     g1_affine* table = nullptr;   // [W][n] : table[w*n + i] = 2^(c*w) * P_i  (affine, Montgomery)
     uint32_t log_n = 0, c = 0, W = 0;
+    // second expansion with a narrow window for columns of small values (witness cells, lookup inputs):
+    // a 29-bit value has 3 signed digits at c = 10 or at c = 13 alike, but c = 10 has 512 buckets to
+    // reduce per column instead of 4096, and the bucket reduction is what such columns pay for
+    g1_affine* table_s = nullptr;
+    uint32_t c_s = 0, W_s = 0;
     bool loaded = false;
     bool shared = false;          // table owned by another context (zkfhe_share_srs)
 };
@@ -30,6 +35,7 @@ struct MsmBasis {
 struct NttDomain {
     fr_t* tw_fwd = nullptr;   // omega^i,  i < n
     fr_t* tw_inv = nullptr;   // omega^-i, i < n
+    fr_t* tw_inv_s = nullptr; // omega^-i / n, i < n (4-step twiddles of the inverse transform)
     fr_t n_inv;               // host copy (Montgomery), passed by value to kernels
 };
 
@@ -138,7 +144,7 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
             uint64_t out_stride, uint32_t log_n, uint32_t batch, int inverse, int coset);
 int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n);
 int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log_n, uint32_t batch,
-            int which, g1_affine* d_out);
+            int which, g1_affine* d_out, int small_values = 0);
 int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d_g, g1_affine* d_gl);
 int fr_convert(zkfhe_ctx* ctx, fr_t* d, uint64_t count, int to_montgomery);
 int points_to_canonical(zkfhe_ctx* ctx, g1_affine* d_pts, uint32_t count);

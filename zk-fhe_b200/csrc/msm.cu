@@ -407,8 +407,11 @@ static uint32_t pick_window(uint32_t log_n) {
 
 int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n) {
     MsmBasis& B = ctx->basis[which];
-    if (B.table && !B.shared) ZK_CUDA(ctx, cudaFree(B.table));
-    B.table = nullptr; B.loaded = false; B.shared = false;
+    if (B.table && !B.shared) {
+        ZK_CUDA(ctx, cudaFree(B.table));
+        if (B.table_s) ZK_CUDA(ctx, cudaFree(B.table_s));
+    }
+    B.table = B.table_s = nullptr; B.loaded = false; B.shared = false;
     B.log_n = log_n;
     B.c = pick_window(log_n);
     B.W = (255 + B.c - 1) / B.c;
@@ -417,19 +420,29 @@ int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t
     ZK_CUDA(ctx, cudaMalloc(&B.table, n * B.W * sizeof(g1_affine)));
     k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, B.table, (uint32_t)n, B.c, B.W);
     ZK_CHECK_LAUNCH(ctx);
+    B.c_s = B.W_s = 0;
+    if (log_n >= 11) {                   // narrow-window expansion for small-valued columns
+        B.c_s = B.c - 3;
+        B.W_s = (255 + B.c_s - 1) / B.c_s;
+        ZK_CUDA(ctx, cudaMalloc(&B.table_s, n * B.W_s * sizeof(g1_affine)));
+        k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, B.table_s, (uint32_t)n, B.c_s, B.W_s);
+        ZK_CHECK_LAUNCH(ctx);
+    }
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     B.loaded = true;
     return ZKFHE_OK;
 }
 
 int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log_n, uint32_t batch, int which,
-            g1_affine* d_out) {
+            g1_affine* d_out, int small_values) {
     if (which < 0 || which > 1) return fail(ctx, ZKFHE_ERR_ARG, "msm: basis must be 0 or 1");
     MsmBasis& B = ctx->basis[which];
     if (!B.loaded) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
     if (log_n != B.log_n) return fail(ctx, ZKFHE_ERR_ARG, "msm: log_n=%u but SRS has k=%u", log_n, B.log_n);
     if (batch == 0) return ZKFHE_OK;
-    const uint32_t n = 1u << log_n, c = B.c, W = B.W, NB = 1u << (c - 1);
+    const bool narrow = small_values && B.table_s;
+    const g1_affine* table = narrow ? B.table_s : B.table;
+    const uint32_t n = 1u << log_n, c = narrow ? B.c_s : B.c, W = narrow ? B.W_s : B.W, NB = 1u << (c - 1);
     const uint64_t max_refs = (uint64_t)n * W;
     const uint32_t SEG = pick_seg(batch);
     const uint64_t max_thr = (max_refs + SEG - 1) / SEG;     // accumulate threads per column
@@ -478,7 +491,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
         dim3 grid((uint32_t)((max_thr + 127) / 128), nb);
-        k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(B.table, c, SEG, boff, soff, sorted, max_refs, partial, max_segs);
+        k_msm_accumulate<<<grid, 128, 0, ctx->stream>>>(table, c, SEG, boff, soff, sorted, max_refs, partial, max_segs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FOLD, 0));

@@ -11,16 +11,24 @@
 //           matrix (input index i1*C + i2), then the twiddle w_n^(i2*k1);
 //   pass B  R independent C-point transforms along the rows, stored transposed
 //           (output index k1 + R*k2).
-// Each CTA keeps a tile of T = 1024 (or 2048) field elements in shared memory
-// and runs all of a pass's butterfly stages there, so one element moves
-// HBM->SM->HBM once per pass: 2 x 64 B per element per transform against 64 B
-// algorithmic.  In pass A a tile is R rows x L adjacent columns (L*32-byte
-// contiguous runs); in pass B it is L whole rows (C*32-byte runs in, L*32-byte
-// runs out).  n <= 2048 is a single pass-B launch with L = 1.
+// A CTA owns a tile of T = 1024 (or 2048) field elements: in pass A R rows x L
+// adjacent columns (L*32-byte contiguous runs), in pass B L whole rows.  n <= 2048
+// is a single pass-B launch with L = 1.
+//
+// Inside a pass the log2(R) radix-2 DIT stages are grouped into ROUNDS of three
+// (radix-8 in registers: 8 elements, 12 butterflies, 7 twiddles per thread).  The
+// first round reads its operands straight from HBM (bit-reversed gather) and the
+// last one writes straight back, so a 6-stage pass exchanges data through shared
+// memory once and a 7/8-stage pass twice, instead of once per stage; an element
+// moves HBM->SM->HBM once per pass: 2 x 64 B per element per transform against
+// 64 B algorithmic.  Shared memory holds the tile as two 16-byte planes (low and
+// high halves of every element) so that a quarter-warp's 128-bit accesses cover
+// 32 distinct banks.
 //
 // Fused into the passes: zero extension of a short input (coeff_to_extended),
 // the coset pre-multiplication zeta^(i mod 3), the n^-1 scaling of the inverse
-// and the coset post-multiplication zeta^-(i mod 3).
+// (folded into the 4-step twiddle table for two-pass transforms) and the coset
+// post-multiplication zeta^-(i mod 3).
 #include "common.cuh"
 
 namespace zkfhe {
@@ -44,12 +52,16 @@ __global__ void k_n_inv(fr_t* out, uint32_t log_n) {
 struct NttPass {
     const fr_t* in;
     fr_t* out;
-    const fr_t* tw;
+    const fr_t* tw;                   // w^i (forward) or w^-i (inverse), i < n: butterfly twiddles
+    const fr_t* tw4;                  // 4-step twiddles of pass A: tw, or w^-i * n^-1 for the inverse
     uint64_t in_stride, out_stride;   // elements between consecutive batch columns
     uint32_t log_n, log_r, log_l;
     uint32_t mode;                    // 0: pass A (strided columns), 1: pass B / single (rows)
     uint32_t in_len;                  // input elements with index >= in_len read as zero
     uint32_t pre_coset, post_scale, post_coset;
+    uint32_t n_rounds;
+    uint32_t zero_stages;             // leading stages of round 0 whose second operand is structurally zero (zero-extended input)
+    uint8_t rounds[8];                // stages per round (3, 2, 1; a trailing 0 = plain copy-out)
     fr_t n_inv, zeta, zeta2;
 };
 
@@ -57,78 +69,126 @@ extern __shared__ uint4 ntt_smem[];
 
 __device__ __forceinline__ uint32_t brev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
 
-__global__ void __launch_bounds__(1024) k_ntt_pass(const NttPass p) {
-    fr_t* S = reinterpret_cast<fr_t*>(ntt_smem);
-    const uint32_t R = 1u << p.log_r, L = 1u << p.log_l, T = R << p.log_l;
-    const uint32_t n = 1u << p.log_n;
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const fr_t* in = p.in + (uint64_t)blockIdx.y * p.in_stride;
-    fr_t* out = p.out + (uint64_t)blockIdx.y * p.out_stride;
-    const uint32_t lmask = L - 1;
+__device__ __forceinline__ fr_t smem_load(const uint4* lo, const uint4* hi, uint32_t i) {
+    uint4 a = lo[i], b = hi[i];
+    fr_t r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void smem_store(uint4* lo, uint4* hi, uint32_t i, const fr_t& v) {
+    lo[i] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    hi[i] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+
+// LR radix-2 DIT stages (stage indices s .. s+LR-1 of the sub-transform) on 2^LR elements held in
+// registers: x[a] sits at transform position t0 + a * 2^s, j = t0 mod 2^s.
+template <int LR>
+__device__ __forceinline__ void dit_round(fr_t* x, uint32_t j, uint32_t s, uint32_t log_n, const fr_t* __restrict__ tw,
+                                          uint32_t zero_stages) {
+#pragma unroll
+    for (int i = 0; i < LR; i++) {
+        const uint32_t h = 1u << i;
+#pragma unroll
+        for (int a = 0; a < (1 << LR); a++) {
+            if (a & h) continue;
+            if ((uint32_t)i < zero_stages) { x[a + h] = x[a]; continue; }     // u + 0*w = u - 0*w = u
+            const uint32_t lowa = (uint32_t)a & (h - 1);
+            fr_t v = x[a + h];
+            // exponent of w_(2^(s+i+1)); it is zero for every lane exactly when s == 0 and lowa == 0
+            if (!(s == 0 && lowa == 0)) v = mul(v, fe_load_nc(tw + ((uint64_t)(j + (lowa << s)) << (log_n - s - i - 1))));
+            const fr_t u = x[a];
+            x[a] = add(u, v);
+            x[a + h] = sub(u, v);
+        }
+    }
+}
+
+template <int LR>
+__device__ __forceinline__ void ntt_round(const NttPass& p, uint4* Slo, uint4* Shi, uint32_t s, bool first, bool last,
+                                          const fr_t* __restrict__ in, fr_t* __restrict__ out) {
+    const uint32_t T = 1u << (p.log_r + p.log_l), lmask = (1u << p.log_l) - 1;
     const uint32_t log_c = p.log_n - p.log_r;          // pass A: columns; pass B: rows of the matrix
     const uint32_t base = blockIdx.x << p.log_l;       // first column (A) / first row (B) of this tile
-
-    // ---- load tile, bit-reversing the transform index ---------------------------------
-    for (uint32_t e = tid; e < T; e += nt) {
-        uint32_t t, l, g;
-        if (p.mode == 0) { l = e & lmask; t = e >> p.log_l; g = (t << log_c) + base + l; }
-        else             { t = e & (R - 1); l = e >> p.log_r; g = ((base + l) << p.log_r) + t; }
-        fr_t v;
-        if (g < p.in_len) {
-            v = fe_load(in + g);
-            if (p.pre_coset) {
-                uint32_t m3 = g % 3u;
-                if (m3 == 1) v = mul(v, p.zeta);
-                else if (m3 == 2) v = mul(v, p.zeta2);
+    for (uint32_t q = threadIdx.x; q < (T >> LR); q += blockDim.x) {
+        const uint32_t l = q & lmask, u = q >> p.log_l;
+        const uint32_t j = u & ((1u << s) - 1);
+        const uint32_t t0 = ((u >> s) << (s + LR)) + j;
+        fr_t x[1 << LR];
+#pragma unroll
+        for (int a = 0; a < (1 << LR); a++) {
+            const uint32_t t = t0 + ((uint32_t)a << s);
+            if (first) {
+                const uint32_t tn = brev(t, p.log_r);                 // DIT consumes its input in bit-reversed order
+                const uint32_t g = p.mode == 0 ? (tn << log_c) + base + l : ((base + l) << p.log_r) + tn;
+                if (g < p.in_len) {
+                    fr_t v = fe_load(in + g);
+                    if (p.pre_coset) {
+                        const uint32_t m3 = g % 3u;
+                        if (m3 == 1) v = mul(v, p.zeta);
+                        else if (m3 == 2) v = mul(v, p.zeta2);
+                    }
+                    x[a] = v;
+                } else {
+                    x[a] = fe_zero<FR>();
+                }
+            } else {
+                x[a] = smem_load(Slo, Shi, (t << p.log_l) + l);
             }
-        } else {
-            v = fe_zero<FR>();
         }
-        fe_store(S + ((brev(t, p.log_r) << p.log_l) + l), v);
-    }
-    __syncthreads();
-
-    // ---- log_r radix-2 DIT stages in shared memory -------------------------------------
-    const uint32_t half = T >> 1;
-    for (uint32_t s = 0; s < p.log_r; s++) {
-        const uint32_t m = 1u << s;
-        for (uint32_t b = tid; b < half; b += nt) {
-            uint32_t l = b & lmask;
-            uint32_t bf = b >> p.log_l;
-            uint32_t j = bf & (m - 1);
-            uint32_t i0 = ((bf >> s) << (s + 1)) + j;
-            fr_t* p0 = S + ((i0 << p.log_l) + l);
-            fr_t* p1 = p0 + (m << p.log_l);
-            fr_t u = fe_load(p0);
-            fr_t v = fe_load(p1);
-            if (j) v = mul(v, fe_load_nc(p.tw + ((uint64_t)j << (p.log_n - s - 1))));
-            fe_store(p0, add(u, v));
-            fe_store(p1, sub(u, v));
-        }
-        __syncthreads();
-    }
-
-    // ---- store ------------------------------------------------------------------------
-    for (uint32_t e = tid; e < T; e += nt) {
-        uint32_t l = e & lmask, t = e >> p.log_l, g;
-        fr_t v = fe_load(S + e);
-        if (p.mode == 0) {
-            uint32_t col = base + l;
-            g = (t << log_c) + col;
-            uint32_t tw_idx = col * t;                  // < n
-            if (tw_idx) v = mul(v, fe_load_nc(p.tw + tw_idx));
-        } else {
-            g = (base + l) + (t << log_c);
-            if (p.post_coset) {
-                uint32_t m3 = g % 3u;                   // zeta^-g = zeta^((3 - g%3) % 3)
-                if (m3 == 1) v = mul(v, p.zeta2);
-                else if (m3 == 2) v = mul(v, p.zeta);
+        dit_round<LR>(x, j, s, p.log_n, p.tw, first ? p.zero_stages : 0);
+#pragma unroll
+        for (int a = 0; a < (1 << LR); a++) {
+            const uint32_t t = t0 + ((uint32_t)a << s);
+            if (last) {
+                fr_t v = x[a];
+                uint32_t g;
+                if (p.mode == 0) {
+                    const uint32_t col = base + l;
+                    g = (t << log_c) + col;
+                    const uint32_t tw_idx = col * t;            // < n
+                    if (tw_idx || p.tw4 != p.tw) v = mul(v, fe_load_nc(p.tw4 + tw_idx));
+                } else {
+                    g = (base + l) + (t << log_c);
+                    if (p.post_coset) {
+                        const uint32_t m3 = g % 3u;             // zeta^-g = zeta^((3 - g%3) % 3)
+                        if (m3 == 1) v = mul(v, p.zeta2);
+                        else if (m3 == 2) v = mul(v, p.zeta);
+                    }
+                    if (p.post_scale) v = mul(v, p.n_inv);
+                }
+                fe_store(out + g, v);
+            } else {
+                smem_store(Slo, Shi, (t << p.log_l) + l, x[a]);
             }
-            if (p.post_scale) v = mul(v, p.n_inv);
         }
-        fe_store(out + g, v);
     }
-    (void)n;
+}
+
+__global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
+    const uint32_t T = 1u << (p.log_r + p.log_l);
+    uint4* Slo = ntt_smem;
+    uint4* Shi = ntt_smem + T;
+    const fr_t* in = p.in + (uint64_t)blockIdx.y * p.in_stride;
+    fr_t* out = p.out + (uint64_t)blockIdx.y * p.out_stride;
+    uint32_t s = 0;
+    for (uint32_t ri = 0; ri < p.n_rounds; ri++) {
+        const uint32_t r = p.rounds[ri];
+        const bool first = ri == 0, last = ri + 1 == p.n_rounds;
+        if (r == 3) ntt_round<3>(p, Slo, Shi, s, first, last, in, out);
+        else if (r == 2) ntt_round<2>(p, Slo, Shi, s, first, last, in, out);
+        else if (r == 1) ntt_round<1>(p, Slo, Shi, s, first, last, in, out);
+        else ntt_round<0>(p, Slo, Shi, s, first, last, in, out);
+        s += r;
+        if (!last) __syncthreads();
+    }
+}
+
+// tw4[i] = w^-i * n^-1: the inverse transform's scaling rides on the 4-step twiddle
+__global__ void k_scale_twiddles(const fr_t* tw, fr_t* out, uint32_t n, const fr_t* n_inv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_store(out + i, mul(fe_load(tw + i), fe_load(n_inv)));
 }
 
 int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out) {
@@ -147,6 +207,9 @@ int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out) {
     ZK_CHECK_LAUNCH(ctx);
     k_n_inv<<<1, 1, 0, ctx->stream>>>(d_ninv, log_n);
     ZK_CHECK_LAUNCH(ctx);
+    ZK_CUDA(ctx, cudaMalloc(&d.tw_inv_s, n * sizeof(fr_t)));
+    k_scale_twiddles<<<blocks, 256, 0, ctx->stream>>>(d.tw_inv, d.tw_inv_s, (uint32_t)n, d_ninv);
+    ZK_CHECK_LAUNCH(ctx);
     ZK_CUDA(ctx, cudaMemcpyAsync(&d.n_inv, d_ninv, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ZK_CUDA(ctx, cudaFree(d_ninv));
@@ -155,10 +218,28 @@ int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out) {
     return ZKFHE_OK;
 }
 
-static int launch_pass(zkfhe_ctx* ctx, const NttPass& p, uint32_t tiles, uint32_t batch) {
-    uint32_t T = 1u << (p.log_r + p.log_l);
-    uint32_t threads = T / 2 < 32 ? 32 : (T / 2 > 1024 ? 1024 : T / 2);
-    size_t smem = (size_t)T * sizeof(fr_t);
+static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch) {
+    const uint32_t T = 1u << (p.log_r + p.log_l);
+    // rounds of three stages; a remainder of one is taken as 2 + 2 so no round is a lone radix-2
+    uint32_t left = p.log_r, nr = 0;
+    while (left > 4 || left == 3) { p.rounds[nr++] = 3; left -= 3; }
+    if (left == 4) { p.rounds[nr++] = 2; p.rounds[nr++] = 2; }
+    else if (left) p.rounds[nr++] = (uint8_t)left;
+    if (nr < 2) p.rounds[nr++] = 0;      // never load and store in the same round: an in-place pass would race
+    p.n_rounds = nr;
+    // pass A of a zero-extended transform: rows i1 >= in_len / C are zero, i.e. (bit-reversed) every DIT position
+    // whose low z bits are not all zero -- the first z stages only copy
+    p.zero_stages = 0;
+    if (p.mode == 0) {
+        const uint32_t log_c = p.log_n - p.log_r;
+        uint32_t z = 0;
+        while (z < p.rounds[0] && z < p.log_r && ((uint64_t)p.in_len << (z + 1)) <= ((uint64_t)1 << p.log_n) &&
+               (p.in_len >> log_c) << log_c == p.in_len)
+            z++;
+        p.zero_stages = z;
+    }
+    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8);
+    const size_t smem = (size_t)T * sizeof(fr_t);
     // process-wide attribute: always the fixed maximum (2048-element tile), never this call's size
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int)sizeof(fr_t)));
     dim3 grid(tiles, batch);
@@ -176,6 +257,7 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
     ZK_TRY(ntt_domain(ctx, log_n, &dom));
     NttPass p{};
     p.tw = inverse ? dom->tw_inv : dom->tw_fwd;
+    p.tw4 = inverse ? dom->tw_inv_s : dom->tw_fwd;
     p.log_n = log_n;
     p.n_inv = dom->n_inv;
     p.zeta = fr_t{ZKFHE_FR_ZETA_MONT};
@@ -200,14 +282,16 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         // pass B: tmp -> out
         p.in = tmp; p.out = d_out; p.in_stride = (uint64_t)1 << log_n; p.out_stride = out_stride;
         p.log_r = log_c; p.log_l = log_t - log_c < log_ra ? log_t - log_c : log_ra; p.mode = 1; p.in_len = 1u << log_n;
-        p.pre_coset = 0; p.post_scale = inverse; p.post_coset = (inverse && coset);
+        p.pre_coset = 0; p.post_scale = 0 /* n^-1 already applied by pass A's twiddles */; p.post_coset = (inverse && coset);
         ZK_TRY(launch_pass(ctx, p, 1u << (log_ra - p.log_l), batch));
     }
     ZK_TRY(timed_end(ctx));
     {   // products issued: one per butterfly, plus the per-element 4-step twiddle, coset and n^-1 factors (x3 = thirds)
         const uint64_t elems = (uint64_t)batch << log_n;
-        uint64_t thirds = (log_n > 11 ? 3 : 0) + (coset ? 2 : 0) + (inverse ? 3 : 0);
-        ctx->ntt_products += elems / 2 * log_n + elems * thirds / 3;
+        uint64_t thirds = (log_n > 11 ? 3 : 0) + (coset ? 2 : 0) + (inverse && log_n <= 11 ? 3 : 0);
+        uint32_t z = 0;                  // copy-only stages of a zero-extended pass A issue no products
+        while (log_n > 11 && z < 3 && ((uint64_t)in_len << (z + 1)) <= ((uint64_t)1 << log_n)) z++;
+        ctx->ntt_products += elems / 2 * (log_n - z) + elems * thirds / 3;
     }
     return ZKFHE_OK;
 }

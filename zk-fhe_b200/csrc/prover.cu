@@ -490,11 +490,12 @@ namespace zkfhe {
 static inline fr_t dev(const Fr& a) { fr_t r; memcpy(r.v, a.l, 32); return r; }
 
 // commit `count` Lagrange-basis (basis 1) or coefficient-basis (basis 0) columns and write the points
-static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count, int basis) {
+// (`small_values`: the columns hold witness cells / lookup inputs, mostly far below the field size)
+static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count, int basis, int small_values = 0) {
     zkfhe_ctx* ctx = pr->ctx;
     g1_affine* d_pts;
     ZK_TRY(ws_get(ctx, "pr_points", (size_t)count * sizeof(g1_affine), (void**)&d_pts));
-    ZK_TRY(msm_run(ctx, d_cols, pr->pk->n, pr->pk->k, count, basis, d_pts));
+    ZK_TRY(msm_run(ctx, d_cols, pr->pk->n, pr->pk->k, count, basis, d_pts, small_values));
     ZK_TRY(points_to_canonical(ctx, d_pts, count));
     std::vector<std::array<uint64_t, 8>> h(count);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pts, (size_t)count * 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -621,7 +622,7 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     std::vector<ColSrc> src;
     for (uint32_t j = 0; j < pk->n_gate0; j++) src.push_back(ColSrc{w->adv[0].p, pk->cut[0].start[j], pk->cut[0].rows[j]});
     ZK_TRY(fill_advice(pr, w, 0, src));
-    ZK_TRY(commit_and_write(pr, pr->P, pk->n_gate0, 1));
+    ZK_TRY(commit_and_write(pr, pr->P, pk->n_gate0, 1, 1));
     pr->gamma_rlc = pr->tr.squeeze();
     memcpy(h_gamma_out, pr->gamma_rlc.l, 32);
     pr->stage = 1;
@@ -667,7 +668,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
             src.push_back(ColSrc{w->lk[1].p, start, rows});
         }
         ZK_TRY(fill_advice(pr, w, pk->n_gate0, src));
-        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pk->n_gate0 * n, pk->n_advice - pk->n_gate0, 1));
+        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pk->n_gate0 * n, pk->n_advice - pk->n_gate0, 1, 1));
     }
     pr->theta = pr->tr.squeeze();
     pr->mark(1);
@@ -679,7 +680,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         k_lookup_permute<<<pk->n_lookup, 1024, 3 * T * 4, ctx->stream>>>(
             pr->P + (size_t)pr->lookup_adv_base * n, n, pr->P + (size_t)pr->ap_base * n, n, n, usable, T, pr->blind, status);
         ZK_CHECK_LAUNCH(ctx);
-        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->ap_base * n, 2 * pk->n_lookup, 1));
+        ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->ap_base * n, 2 * pk->n_lookup, 1, 1));
         uint32_t st = 0;
         ZK_CUDA(ctx, cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
         ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
