@@ -275,6 +275,26 @@ int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32);
 void zkfhe_prover_free(zkfhe_prover* pr);
 void zkfhe_proof_free(uint8_t* proof);
 
+/* ---- verify (reference `verify` subcommand, README.md:48-54) --------------------------------
+ * The pairing check halo2-axiom's VerifierSHPLONK ends with: is prod_i e(P_i, Q_i) == 1 ?
+ * P_i are 64-byte G1 affine points (x | y), Q_i 128-byte G2 affine points (x.c0 | x.c1 | y.c0 | y.c1,
+ * Fq2 = Fq[u]/(u^2+1)); every coordinate Montgomery (R = 2^256), identity = all zeros.  Host
+ * arithmetic: one check per proof. */
+int zkfhe_pairing_check(const uint8_t* g1_points, const uint8_t* g2_points, uint32_t count, int* is_one);
+/* [tau]_2 of the test SRS made by zkfhe_srs_setup (halo2 `ParamsKZG::setup` keeps s_g2 beside the G1
+ * powers): tau as a Montgomery Fr element in, 128 bytes (x.c0 | x.c1 | y.c0 | y.c1, Montgomery) out. */
+int zkfhe_srs_g2(const uint8_t* tau_mont32, uint8_t* out128);
+/* The verifying key as bytes -- the reference's data/<name>.vk written by `keygen`: the layout numbers
+ * of the circuit and the commitments of the fixed columns.  Call with buf = NULL to get the size. */
+int zkfhe_vk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed);
+/* The reference's `verify`: replay the transcript, check every gate / permutation / lookup identity at
+ * the challenge point, fold the SHPLONK multi-open into one MSM over the proof's and the key's
+ * commitments (GPU) and finish with the pairing check (host).  `instances`: n canonical 32-byte
+ * little-endian scalars; `s_g2`: [tau]_2 as above.  Returns ZKFHE_OK with *accepted = 1 or 0 (the
+ * reason for a rejection is zkfhe_last_error); error codes are for malformed arguments only. */
+int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t* instances, uint32_t n_instances,
+                 const uint8_t* proof, size_t proof_len, const uint8_t* s_g2, int transcript_kind, int* accepted);
+
 /* ---- timing hook -------------------------------------------------------------------------
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last
  * NTT / MSM call: the butterfly passes for NTT, the bucket-accumulation kernel for MSM. */

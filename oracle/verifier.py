@@ -66,7 +66,7 @@ def _msm(points, scalars):
     return curve.g1_from_mont_bytes(out[0].tobytes())
 
 
-def verify(vk, instances, proof, tau, transcript_kind=0):
+def verify(vk, instances, proof, tau, transcript_kind=0, s_g2=None):
     """Raises VerifyError unless `proof` is valid for `instances` under `vk`.  tau: SRS trapdoor."""
     n, k, usable = vk.n, vk.k, vk.usable
     r = R_MOD
@@ -250,6 +250,13 @@ def verify(vk, instances, proof, tau, transcript_kind=0):
     scal += [g_coeff, (-zt) % r]
     F = _msm(scal_pts, scal)
     lhs = curve.g1_add(F, curve.g1_mul(Wp, u))
+    if s_g2 is not None:
+        # the verifier's own check, no trapdoor: e(F + u W', [1]_2) * e(-W', [tau]_2) == 1
+        from . import pairing
+        neg_wp = None if Wp is None else (Wp[0], (-Wp[1]) % curve.P_MOD)
+        if not pairing.pairing_product_is_one([(lhs, pairing.G2_GEN), (neg_wp, s_g2)]):
+            raise VerifyError("KZG opening check failed (pairing)")
+        return True
     rhs = curve.g1_mul(Wp, tau)
     if lhs != rhs:
         raise VerifyError("KZG opening check failed")

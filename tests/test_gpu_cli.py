@@ -1,5 +1,5 @@
 """The `bfv` entrypoint (C++ host mirror of examples/bfv.rs + halo2-scaffold's CLI) through its
-command line, as the reference's README drives it: mock, keygen, prove."""
+command line, as the reference's README drives it: mock, keygen, prove, verify."""
 import json
 import os
 import shutil
@@ -37,6 +37,20 @@ def test_cli_mock_keygen_prove(workdir, golden_dir):
     r = _run(workdir, "--input", "bfv/bfv.in", "prove")
     assert r.returncode == 0 and "Proving time" in r.stdout, r.stderr
     assert os.path.getsize(workdir / "data" / "bfv.snark") > 50_000
+    # README.md:48-54: verify reads data/bfv.vk (keygen) and data/bfv.snark (prove)
+    assert os.path.getsize(workdir / "data" / "bfv.vk") == 72 + 64 * 365
+    r = _run(workdir, "--input", "bfv/bfv.in", "verify")
+    assert r.returncode == 0 and "Snark verified successfully" in r.stdout and "Verification time" in r.stdout, r.stdout + r.stderr
+    snark = bytearray(open(workdir / "data" / "bfv.snark", "rb").read())
+    snark[16 + 32 * 5121 + 64 * 10 + 3] ^= 1                    # one bit of an advice commitment
+    open(workdir / "data" / "bfv.snark", "wb").write(snark)
+    r = _run(workdir, "--input", "bfv/bfv.in", "verify")
+    assert r.returncode == 1 and "REJECTED" in r.stdout
+    snark[16 + 32 * 5121 + 64 * 10 + 3] ^= 1
+    snark[16 + 32 * 7] ^= 2                                      # a public input (a pk0 coefficient)
+    open(workdir / "data" / "bfv.snark", "wb").write(snark)
+    r = _run(workdir, "--input", "bfv/bfv.in", "verify")
+    assert r.returncode == 1 and "REJECTED" in r.stdout
 
 
 def test_cli_mock_rejects_a_tampered_input(workdir):

@@ -100,6 +100,12 @@ def test_prove_bfv_in_and_oracle_verifier_accepts(ctx13, pk13, bfv_input):
     assert inst[:1024] == [int(x) for x in bfv_input["pk0"]]
     vk = _vk(pk13, 109)
     assert verifier.verify(vk, inst, proof, TAU)
+    # the same proof under the real verifier equation: pairing against [tau]_2, no trapdoor
+    from oracle import pairing
+    s_g2 = pairing.g2_mul(pairing.G2_GEN, TAU)
+    assert verifier.verify(vk, inst, proof, None, s_g2=s_g2)
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, inst, proof, None, s_g2=pairing.g2_mul(pairing.G2_GEN, TAU + 1))
     # deterministic for a fixed seed, different for another seed (blinding)
     proof2, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
     assert proof2 == proof
@@ -118,6 +124,45 @@ def test_prove_bfv_in_and_oracle_verifier_accepts(ctx13, pk13, bfv_input):
         verifier.verify(vk, bad_inst, proof, TAU)
     with pytest.raises(verifier.VerifyError):
         verifier.verify(vk, inst, proof, TAU + 1)                      # wrong SRS
+
+
+def test_product_verifier_agrees_with_oracle_verifier(ctx13, pk13, bfv_input):
+    """zkfhe_verify (the reference's `verify` subcommand: transcript replay + identities on the host, one MSM on
+    the GPU, pairing on the host) accepts what the oracle verifier accepts and rejects what it rejects."""
+    from zk_fhe_b200 import prover
+    proof, inst = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    vkb, s_g2 = pk13.vk_bytes(), ctx13.srs_g2(TAU)
+    vk = _vk(pk13, 109)
+    assert len(vkb) == 72 + 64 * pk13.info["n_fixed"]
+    assert prover.verify(ctx13, vkb, inst, proof, s_g2)
+    assert verifier.verify(vk, inst, proof, TAU)
+    # verifying borrows the commitment-key slot for its MSM and must give it back intact
+    proof2, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    assert proof2 == proof
+    rng = random.Random(11)
+    offsets = [5, 64 * 3 + 40, 64 * 197 + 3, len(proof) // 2, len(proof) - 100, len(proof) - 1]
+    offsets += [rng.randrange(len(proof)) for _ in range(6)]
+    for off in offsets:
+        bad = bytearray(proof)
+        bad[off] ^= 1 << rng.randrange(8)
+        assert not prover.verify(ctx13, vkb, inst, bytes(bad), s_g2), off
+        assert "rejected" in ctx13.last_rejection
+        with pytest.raises(verifier.VerifyError):
+            verifier.verify(vk, inst, bytes(bad), TAU)
+    assert not prover.verify(ctx13, vkb, inst, proof[:-1], s_g2)
+    assert not prover.verify(ctx13, vkb, inst, proof + b"\0", s_g2)
+    bad_inst = list(inst)
+    bad_inst[2048 + 17] = (bad_inst[2048 + 17] + 1) % 536870909
+    assert not prover.verify(ctx13, vkb, bad_inst, proof, s_g2)
+    assert not prover.verify(ctx13, vkb, inst[:-1], proof, s_g2)
+    assert not prover.verify(ctx13, vkb, inst, proof, ctx13.srs_g2(TAU + 1))          # another SRS
+    bad_vk = bytearray(vkb)
+    bad_vk[72 + 64 * 200 + 7] ^= 4                                                      # a fixed commitment
+    assert not prover.verify(ctx13, bytes(bad_vk), inst, proof, s_g2)
+    import zk_fhe_b200
+    with pytest.raises(zk_fhe_b200.ZkfheError):
+        prover.verify(ctx13, vkb[:-3], inst, proof, s_g2)                               # malformed key: an error, not a verdict
+    assert prover.verify(ctx13, vkb, inst, proof, s_g2)
 
 
 def test_proof_of_a_wrong_ciphertext_is_rejected(ctx13, pk13, bfv_input):
@@ -201,6 +246,8 @@ def test_small_circuit_end_to_end_both_transcripts(transcript):
     proof, inst = _prove(ctx, pk, inp, bytes(32), params, transcript)
     vk = _vk(pk, unusable)
     assert verifier.verify(vk, inst, proof, TAU, transcript_kind=transcript)
+    assert prover.verify(ctx, pk.vk_bytes(), inst, proof, ctx.srs_g2(TAU), transcript=transcript)
+    assert not prover.verify(ctx, pk.vk_bytes(), inst, proof, ctx.srs_g2(TAU), transcript=1 - transcript)
     with pytest.raises(verifier.VerifyError):
         verifier.verify(vk, inst, proof, TAU, transcript_kind=1 - transcript)
     ctx.close()

@@ -1,0 +1,73 @@
+"""Host-side pieces of the `verify` path that need no GPU: zkfhe_pairing_check and zkfhe_srs_g2 of
+libzkfhe_b200.so against the oracle's pairing / G2 arithmetic."""
+import ctypes
+
+from oracle import curve, pairing
+from oracle.field import P_MOD, R_MOD
+
+import zk_fhe_b200
+from zk_fhe_b200.capi import _addr, fr_mont_bytes
+
+
+def _fq(x):
+    return ((x << 256) % P_MOD).to_bytes(32, "little")
+
+
+def _g1(p):
+    return bytes(64) if p is None else _fq(p[0]) + _fq(p[1])
+
+
+def _g2(q):
+    return bytes(128) if q is None else _fq(q[0][0]) + _fq(q[0][1]) + _fq(q[1][0]) + _fq(q[1][1])
+
+
+def _check(pairs):
+    lib = zk_fhe_b200.load_library()
+    g1 = bytearray(b"".join(_g1(p) for p, _ in pairs))
+    g2 = bytearray(b"".join(_g2(q) for _, q in pairs))
+    out = ctypes.c_int(-1)
+    rc = lib.zkfhe_pairing_check(_addr(g1), _addr(g2), len(pairs), ctypes.byref(out))
+    assert rc == 0
+    return bool(out.value)
+
+
+def test_pairing_check_agrees_with_oracle_on_products():
+    G = curve.G1_GEN
+    neg_g = (G[0], (-G[1]) % P_MOD)
+    for a in (1, 2, 0xABCDEF123456789, R_MOD - 5):
+        good = [(curve.g1_mul(G, a), pairing.G2_GEN), (neg_g, pairing.g2_mul(pairing.G2_GEN, a))]
+        bad = [(curve.g1_mul(G, a + 1), pairing.G2_GEN), (neg_g, pairing.g2_mul(pairing.G2_GEN, a))]
+        assert _check(good) and pairing.pairing_product_is_one(good)
+        assert not _check(bad) and not pairing.pairing_product_is_one(bad)
+    assert _check([(None, pairing.G2_GEN), (neg_g, None)])           # identities contribute 1
+    assert not _check([(G, pairing.G2_GEN)])                           # non-degenerate
+    assert _check([])
+
+
+def test_pairing_check_kzg_identity():
+    tau, z = 0x5EED5EED5EED, 0x1234
+    coeffs = [11, 22, 33, 44]
+    ev = lambda at: sum(c * pow(at, i, R_MOD) for i, c in enumerate(coeffs)) % R_MOD
+    c_pt = curve.g1_mul(curve.G1_GEN, ev(tau))
+    w_pt = curve.g1_mul(curve.G1_GEN, (ev(tau) - ev(z)) * pow(tau - z, -1, R_MOD) % R_MOD)
+    lhs = curve.g1_add(curve.g1_add(c_pt, curve.g1_mul(curve.G1_GEN, (-ev(z)) % R_MOD)), curve.g1_mul(w_pt, z))
+    neg_w = (w_pt[0], (-w_pt[1]) % P_MOD)
+    assert _check([(lhs, pairing.G2_GEN), (neg_w, pairing.g2_mul(pairing.G2_GEN, tau))])
+    assert not _check([(lhs, pairing.G2_GEN), (neg_w, pairing.g2_mul(pairing.G2_GEN, tau + 1))])
+
+
+def test_pairing_check_rejects_unreduced_coordinates():
+    lib = zk_fhe_b200.load_library()
+    g1 = bytearray(b"\xff" * 64)
+    g2 = bytearray(_g2(pairing.G2_GEN))
+    out = ctypes.c_int(-1)
+    assert lib.zkfhe_pairing_check(_addr(g1), _addr(g2), 1, ctypes.byref(out)) == -2
+
+
+def test_srs_g2_matches_oracle():
+    lib = zk_fhe_b200.load_library()
+    for tau in (1, 2, 0x5EED5EED5EED5EED5EED5EED5EED, R_MOD - 1):
+        out = bytearray(128)
+        t = fr_mont_bytes(tau)
+        assert lib.zkfhe_srs_g2(_addr(t), _addr(out)) == 0
+        assert bytes(out) == _g2(pairing.g2_mul(pairing.G2_GEN, tau))

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkfhe_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu", "verifier.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     if (not force and os.path.exists(LIB) and os.path.exists(stamp_path)
             and open(stamp_path).read() == stamp):
         return LIB
-    for gen in ("gen_ff_ptx.py", "gen_poseidon.py"):
+    for gen in ("gen_ff_ptx.py", "gen_poseidon.py", "gen_pairing_consts.py"):
         subprocess.run([sys.executable, os.path.join(CSRC, gen)], check=True,
                        stdout=None if verbose else subprocess.DEVNULL)
     stamp = _stamp()

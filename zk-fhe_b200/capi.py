@@ -47,6 +47,11 @@ _SIGNATURES = {
     "zkfhe_sync": (_c.c_int, [_c.c_void_p]),
     "zkfhe_launch_count": (_c.c_uint64, [_c.c_void_p]),
     "zkfhe_selftest": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_uint32)]),
+    "zkfhe_pairing_check": (_c.c_int, [_u8p, _u8p, _c.c_uint32, _c.POINTER(_c.c_int)]),
+    "zkfhe_srs_g2": (_c.c_int, [_u8p, _u8p]),
+    "zkfhe_vk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
+    "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,
+                                _c.POINTER(_c.c_int)]),
     "zkfhe_microbench": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint64)]),
     "zkfhe_ntt_fr": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
     "zkfhe_ntt_fr_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
@@ -263,6 +268,13 @@ class Context:
         self._check(self.lib.zkfhe_srs_setup(self.h, k, _addr(t), _addr(g), _addr(gl)))
         self.srs_k = k
         return (bytes(g), bytes(gl)) if want_host_copy else None
+
+    def srs_g2(self, tau):
+        """[tau]_2 of the test SRS (128 bytes, Montgomery): what `verify` pairs against."""
+        t = fr_mont_bytes(tau)
+        out = bytearray(128)
+        self._check(self.lib.zkfhe_srs_g2(_addr(t), _addr(out)))
+        return bytes(out)
 
     def share_srs(self, other):
         """Use `other`'s resident commitment-key tables (same GPU); `other` must stay alive."""

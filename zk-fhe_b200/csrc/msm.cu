@@ -510,4 +510,34 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     return ZKFHE_OK;
 }
 
+// sum_i s_i * P_i over ARBITRARY points (the verifier's commitment combination): the points are expanded into a
+// throw-away fixed-base table and go through the same sort / accumulate / reduce pipeline.  Host buffers in, host
+// point out; Montgomery coordinates, identity = zeros.
+int msm_variable_base(zkfhe_ctx* ctx, const g1_affine* h_points, const fr_t* h_scalars, uint32_t count, g1_affine* h_out) {
+    uint32_t log_n = 4;
+    while ((1u << log_n) < count) log_n++;
+    const size_t n = (size_t)1 << log_n;
+    g1_affine* d_pts;
+    fr_t* d_sc;
+    g1_affine* d_out;
+    ZK_TRY(ws_get(ctx, "vmsm_pts", n * sizeof(g1_affine), (void**)&d_pts));
+    ZK_TRY(ws_get(ctx, "vmsm_sc", n * sizeof(fr_t), (void**)&d_sc));
+    ZK_TRY(ws_get(ctx, "vmsm_out", sizeof(g1_affine), (void**)&d_out));
+    ZK_CUDA(ctx, cudaMemsetAsync(d_pts, 0, n * sizeof(g1_affine), ctx->stream));
+    ZK_CUDA(ctx, cudaMemsetAsync(d_sc, 0, n * sizeof(fr_t), ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_pts, h_points, count * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars, count * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    const MsmBasis saved = ctx->basis[0];
+    ctx->basis[0] = MsmBasis{};
+    int rc = msm_load_basis(ctx, 0, d_pts, log_n);
+    if (rc == ZKFHE_OK) rc = msm_run(ctx, d_sc, n, log_n, 1, 0, d_out, 0);
+    if (rc == ZKFHE_OK && cudaMemcpyAsync(h_out, d_out, sizeof(g1_affine), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = fail(ctx, ZKFHE_ERR_CUDA, "msm_variable_base: copy back failed");
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->basis[0].table) cudaFree(ctx->basis[0].table);
+    if (ctx->basis[0].table_s) cudaFree(ctx->basis[0].table_s);
+    ctx->basis[0] = saved;
+    return rc;
+}
+
 }  // namespace zkfhe

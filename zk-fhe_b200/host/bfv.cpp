@@ -7,10 +7,11 @@
 // <data-path>/<input> (nine arrays of decimal strings, examples/bfv.rs:50-61), keygen writes the
 // pinning to <config-path>/<name>.json (schema of configs/bfv.json), prove writes
 // <data-path>/<name>.snark and prints the proving time.
-// Differences, stated plainly: the proving key is rebuilt in-process (no .pk/.vk files); the SRS is
+// <data-path>/<name>.snark (public instances + proof) and prints the proving time, keygen also writes
+// <data-path>/<name>.vk, and verify reads the two files back and prints the verification time.
+// Differences, stated plainly: the proving key is rebuilt in-process (no .pk file); the SRS is
 // the deterministic *test* setup every time (halo2-scaffold's gen_srs falls back to one too); the
-// proof format is this implementation's own; `verify` is not built into this binary (the
-// independent verifier lives in oracle/verifier.py as test infrastructure).
+// proof / vk / snark formats are this implementation's own.
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,7 @@
 #include <sstream>
 
 #include "zk_fhe.hpp"
+#include "../csrc/host_ff.h"
 
 using namespace zkfhe;
 
@@ -104,9 +106,39 @@ int main(int argc, char** argv) {
         return 2;
     }
     try {
+        uint8_t tau[32];
+        fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau);              // deterministic TEST setup
         if (cmd == "verify") {
-            fprintf(stderr, "verify: not built into this binary; oracle/verifier.py is the independent verifier (test infrastructure)\n");
-            return 3;
+            // reference README.md:48-54: reads the .vk written by keygen and the .snark written by prove
+            auto slurp = [](const std::string& path) {
+                std::ifstream f(path, std::ios::binary);
+                if (!f) throw Error(ZKFHE_ERR_ARG, "cannot open " + path + " (run keygen / prove first)");
+                std::stringstream ss;
+                ss << f.rdbuf();
+                return ss.str();
+            };
+            const std::string vk = slurp(data_path + "/" + name + ".vk"), snark = slurp(data_path + "/" + name + ".snark");
+            if (snark.size() < 16 || memcmp(snark.data(), "ZKFHESN1", 8)) throw Error(ZKFHE_ERR_ARG, "not a zkfhe snark file");
+            uint32_t n_inst, kind;
+            memcpy(&n_inst, snark.data() + 8, 4);
+            memcpy(&kind, snark.data() + 12, 4);
+            if (snark.size() < 16 + 32 * (size_t)n_inst) throw Error(ZKFHE_ERR_ARG, "snark file truncated");
+            Device dev(0);
+            uint8_t s_g2[128];
+            dev.check(zkfhe_srs_g2(tau, s_g2));
+            int ok = 0;
+            auto t0 = std::chrono::steady_clock::now();
+            dev.check(zkfhe_verify(dev.raw(), (const uint8_t*)vk.data(), vk.size(), (const uint8_t*)snark.data() + 16, n_inst,
+                                   (const uint8_t*)snark.data() + 16 + 32 * (size_t)n_inst, snark.size() - 16 - 32 * (size_t)n_inst,
+                                   s_g2, (int)kind, &ok));
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            printf("Verification time: %.3f ms\n", ms);
+            if (!ok) {
+                printf("Snark REJECTED: %s\n", zkfhe_last_error(dev.raw()));
+                return 1;
+            }
+            printf("Snark verified successfully\n");
+            return 0;
         }
         CircuitInput in = parse_input(data_path + "/" + input);
         Device dev(0);
@@ -120,8 +152,6 @@ int main(int argc, char** argv) {
             printf("Mock prover: all constraints satisfied\n");
             return 0;
         }
-        uint8_t tau[32];
-        fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau);              // deterministic TEST setup
         dev.check(zkfhe_srs_setup(dev.raw(), k, tau, nullptr, nullptr));
         // keygen always runs on an input of the same shape with all-zero values (README.md:31-36)
         CircuitInput zeros;
@@ -139,7 +169,12 @@ int main(int argc, char** argv) {
         pin.resize(need - 1);
         if (cmd == "keygen") {
             std::ofstream(config_path + "/" + name + ".json") << pin << "\n";
-            printf("keygen: wrote %s/%s.json\n", config_path.c_str(), name.c_str());
+            size_t vk_len = 0;
+            dev.check(zkfhe_vk_export(pk, nullptr, 0, &vk_len));
+            std::string vk(vk_len, '\0');
+            dev.check(zkfhe_vk_export(pk, (uint8_t*)&vk[0], vk_len, nullptr));
+            std::ofstream(data_path + "/" + name + ".vk", std::ios::binary).write(vk.data(), (std::streamsize)vk.size());
+            printf("keygen: wrote %s/%s.json and %s/%s.vk\n", config_path.c_str(), name.c_str(), data_path.c_str(), name.c_str());
             zkfhe_pk_free(pk);
             return 0;
         }
@@ -166,7 +201,18 @@ int main(int argc, char** argv) {
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             printf("Proving time%s: %.3f ms (%zu proof bytes)\n", pass ? "" : " (cold, incl. one-time allocations)", ms, len);
         }
+        // .snark = "ZKFHESN1" | u32 instances | u32 transcript kind | instances (canonical 32-byte LE) | proof
+        uint32_t info[16];
+        dev.check(zkfhe_pk_info(pk, info));
+        const uint32_t n_inst = info[12], kind = 0;
+        std::vector<host::Fr> inst(n_inst);
+        if (n_inst) dev.check(zkfhe_witness_download(circ.builder().raw(), 4, (uint8_t*)inst.data()));
+        for (auto& v : inst) v = host::from_mont(v);
         std::ofstream out(data_path + "/" + name + ".snark", std::ios::binary);
+        out.write("ZKFHESN1", 8);
+        out.write((const char*)&n_inst, 4);
+        out.write((const char*)&kind, 4);
+        out.write((const char*)inst.data(), (std::streamsize)(32 * (size_t)n_inst));
         out.write((const char*)proof, (std::streamsize)len);
         zkfhe_proof_free(proof);
         zkfhe_prover_free(pr);

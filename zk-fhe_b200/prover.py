@@ -37,6 +37,14 @@ class ProvingKey:
         self.ctx._check(self.ctx.lib.zkfhe_pk_pinning_json(self.h, buf, need.value, None))
         return json.loads(buf.value.decode())
 
+    def vk_bytes(self):
+        """The verifying key as bytes (the reference's data/<name>.vk)."""
+        need = ctypes.c_size_t()
+        self.ctx._check(self.ctx.lib.zkfhe_vk_export(self.h, None, 0, ctypes.byref(need)))
+        buf = bytearray(need.value)
+        self.ctx._check(self.ctx.lib.zkfhe_vk_export(self.h, _addr(buf), need.value, None))
+        return bytes(buf)
+
     def fixed(self, index, form=0):
         """(rows, 4) uint64 Montgomery; form 0 Lagrange, 1 coefficients, 2 extended coset."""
         n = (1 << self.info["k"]) * (4 if form == 2 else 1)
@@ -112,6 +120,17 @@ def prove(pk, circuit_factory, inp, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE
     gamma = pr.phase0(circ.wit)
     circ.phase1(gamma)
     return pr.finish(circ.wit), circ
+
+
+def verify(ctx, vk_bytes, instances, proof, s_g2, transcript=TRANSCRIPT_BLAKE2B):
+    """The reference's `verify` subcommand: True / False.  `instances`: canonical ints; `s_g2`: [tau]_2
+    (Context.srs_g2 for the test SRS).  ctx.last_rejection holds the reason of a rejection."""
+    inst = b"".join(int(v).to_bytes(32, "little") for v in instances)
+    ok = ctypes.c_int(0)
+    ctx._check(ctx.lib.zkfhe_verify(ctx.h, _addr(vk_bytes), len(vk_bytes), _addr(inst) if inst else None, len(instances),
+                                    _addr(proof), len(proof), _addr(s_g2), transcript, ctypes.byref(ok)))
+    ctx.last_rejection = None if ok.value else ctx.lib.zkfhe_last_error(ctx.h).decode()
+    return bool(ok.value)
 
 
 def keygen(witness, k, unusable_rows=109):
