@@ -91,7 +91,8 @@ extern __shared__ uint32_t msm_smem[];
 
 __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
                                                    uint32_t W, uint32_t* bucket_off, uint32_t* rank_out,
-                                                   uint32_t* sorted, uint64_t sorted_stride) {
+                                                   uint32_t* sorted, uint64_t sorted_stride, uint32_t skew_limit,
+                                                   uint32_t* skew_out) {
     const uint32_t NB = 1u << (c - 1);
     uint32_t* cnt = msm_smem;                 // [NB] counts, then running cursors
     __shared__ uint32_t warp_tot[2][32];
@@ -112,11 +113,15 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     // exclusive scans of the counts (entries) and of the non-empty flags (ranks)
     const uint32_t per = (NB + nt - 1) / nt;
     const uint32_t b0 = tid * per;
-    uint32_t sum_e = 0, sum_s = 0;
+    uint32_t sum_e = 0, sum_s = 0, max_c = 0;
     for (uint32_t k = 0; k < per; k++) {
         uint32_t b = b0 + k;
-        if (b < NB) { uint32_t v = cnt[b]; sum_e += v; sum_s += (v != 0); }
+        if (b < NB) { uint32_t v = cnt[b]; sum_e += v; sum_s += (v != 0); max_c = max(max_c, v); }
     }
+    // a column is "skewed" when some bucket is long enough to span many accumulate slices (witness columns
+    // repeating one value thousands of times); only those columns go through the level-0 combine kernel
+    if (__syncthreads_or(max_c > skew_limit) && tid == 0) skew_out[col] = 1;
+    else if (tid == 0) skew_out[col] = 0;
     uint32_t lane = tid & 31, wid = tid >> 5;
     uint32_t inc_e = sum_e, inc_s = sum_s;
     for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -219,9 +224,11 @@ static constexpr uint32_t SUP = 16;
 __global__ void __launch_bounds__(128) k_msm_combine(uint32_t c, uint32_t SEG, const uint32_t* __restrict__ bucket_off,
                                                      const uint32_t* __restrict__ rank_in,
                                                      const g1_xyzz* __restrict__ partial, uint64_t partial_stride,
-                                                     g1_xyzz* partial2, uint64_t partial2_stride) {
+                                                     g1_xyzz* partial2, uint64_t partial2_stride,
+                                                     const uint32_t* __restrict__ skew) {
     const uint32_t NB = 1u << (c - 1);
     const uint32_t col = blockIdx.y, s2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!skew[col]) return;                               // short lists everywhere: k_msm_fold reads level 1 directly
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
     const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
     const uint32_t total = boff[NB];
@@ -248,9 +255,11 @@ __global__ void __launch_bounds__(128) k_msm_combine(uint32_t c, uint32_t SEG, c
 // Reduction, level 1: one thread per group of FOLD consecutive buckets.  Folds the partial sums of
 // each bucket and runs the running-sum trick inside the group:
 //   S_g = sum_b B_b,   A_g = sum_b (b - lo + 1) B_b      (so sum_b (b+1) B_b = A_g + lo * S_g)
-__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uint32_t SEG, const uint32_t* __restrict__ bucket_off,
+__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uint32_t SEG1, const uint32_t* __restrict__ bucket_off,
                                                   const uint32_t* __restrict__ rank_in,
-                                                  const g1_xyzz* __restrict__ partial, uint64_t partial_stride,
+                                                  const g1_xyzz* __restrict__ partial1, uint64_t partial1_stride,
+                                                  const g1_xyzz* __restrict__ partial2, uint64_t partial2_stride,
+                                                  const uint32_t* __restrict__ skew,
                                                   g1_xyzz* group_out /* [col][groups][2] */) {
     const uint32_t NB = 1u << (c - 1);
     const uint32_t groups = NB / fold;
@@ -258,7 +267,10 @@ __global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uin
     if (g >= groups) return;
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
     const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
-    const g1_xyzz* part = partial + (uint64_t)col * partial_stride;
+    // skewed columns were combined SUP slices at a time (level 2); the others are read at level 1
+    const bool sk = skew[col] != 0;
+    const uint32_t SEG = sk ? SEG1 * SUP : SEG1;
+    const g1_xyzz* part = sk ? partial2 + (uint64_t)col * partial2_stride : partial1 + (uint64_t)col * partial1_stride;
     const uint32_t lo = g * fold;
     g1_xyzz running = xyzz_identity(), acc = xyzz_identity();
     for (uint32_t b = lo + fold; b-- > lo;) {
@@ -462,6 +474,8 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     const uint64_t max_segs2 = NB + (max_thr + SUP - 1) / SUP + 1;      // level-2 slots: rank[b] + super-slice
     g1_xyzz* partial2;
     ZK_TRY(ws_get(ctx, "msm_partial2", (size_t)chunk * max_segs2 * sizeof(g1_xyzz), (void**)&partial2));
+    uint32_t* skew;
+    ZK_TRY(ws_get(ctx, "msm_skew", (size_t)chunk * 4, (void**)&skew));
     // reduction shape: groups of 2^log_fold buckets; the final warp owns groups/32 groups per lane.
     // 16 buckets per fold thread and <= 512 groups balance the two dependent chains (2*fold and
     // 3*groups/32 point additions).
@@ -486,7 +500,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
         const fr_t* sc = d_scalars + (uint64_t)done * stride;
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
-        k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs);
+        k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
@@ -496,10 +510,10 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FOLD, 0));
         dim3 cgrid((uint32_t)((max_segs2 + 127) / 128), nb);
-        k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2);
+        k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew);
         ZK_CHECK_LAUNCH(ctx);
         dim3 fgrid((groups + 127) / 128, nb);
-        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG * SUP, boff, soff, partial2, max_segs2, grp);
+        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
