@@ -29,6 +29,7 @@
 // the coset pre-multiplication zeta^(i mod 3), the n^-1 scaling of the inverse
 // (folded into the 4-step twiddle table for two-pass transforms) and the coset
 // post-multiplication zeta^-(i mod 3).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace zkfhe {
@@ -238,10 +239,10 @@ static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch
             z++;
         p.zero_stages = z;
     }
-    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 256 ? 256 : T / 8);
+    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 128 ? 128 : T / 8);     // 136 registers: 3 CTAs of 128 per SM
     const size_t smem = (size_t)T * sizeof(fr_t);
-    // process-wide attribute: always the fixed maximum (2048-element tile), never this call's size
-    ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int)sizeof(fr_t)));
+    // process-wide attribute: always the fixed maximum (4096-element tile), never this call's size
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(fr_t)));
     dim3 grid(tiles, batch);
     k_ntt_pass<<<grid, threads, smem, ctx->stream>>>(p);
     ZK_CHECK_LAUNCH(ctx);
@@ -270,7 +271,12 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         p.pre_coset = (!inverse && coset); p.post_scale = inverse; p.post_coset = (inverse && coset);
         ZK_TRY(launch_pass(ctx, p, 1, batch));
     } else {
-        const uint32_t log_t = log_n > 20 ? 11 : 10;
+        // tile of 1024 elements (3 CTAs of 128 threads per SM).  Measured on B200: 2048- and 4096-element tiles give
+        // longer contiguous runs in pass A but lose 10 % and 55 % to occupancy, at 2^13 .. 2^18 alike.
+        uint32_t log_t = 10;
+        if (const char* e = getenv("ZKFHE_NTT_LOG_T")) log_t = (uint32_t)atoi(e);      // tuning knob (tools/bench_kernels.py)
+        if (log_t < 10) log_t = 10;
+        if (log_t > 12) log_t = 12;
         const uint32_t log_ra = (log_n + 1) / 2, log_c = log_n - log_ra;
         fr_t* tmp;
         ZK_TRY(ws_get(ctx, "ntt_tmp", ((size_t)batch << log_n) * sizeof(fr_t), (void**)&tmp));

@@ -195,8 +195,9 @@ struct GpArgs {
 static constexpr uint32_t GP_THREADS = 1024, GP_PER = 8;     // one tile = 8192 rows; columns are walked tile by tile
 extern __shared__ uint4 gp_smem[];
 __global__ void __launch_bounds__(GP_THREADS) k_grand_product(const GpArgs g) {
-    fr_t* S = reinterpret_cast<fr_t*>(gp_smem);      // [2][GP_THREADS]
+    fr_t* S = reinterpret_cast<fr_t*>(gp_smem);      // [4][GP_THREADS]: two double-buffered scans
     __shared__ fr_t tile_carry;                      // product of all ratios of the previous tiles
+    __shared__ fr_t tile_inv;                        // 1 / (product of this tile's denominators)
     const uint32_t z = blockIdx.x;                   // 0..n_chunks-1: permutation chunks, then lookups
     const bool is_perm = z < g.n_chunks;
     const uint32_t tid = threadIdx.x;
@@ -230,34 +231,39 @@ __global__ void __launch_bounds__(GP_THREADS) k_grand_product(const GpArgs g) {
             num[i - lo] = nu;
             den[i - lo] = de;
         }
-        // batch inversion of this thread's denominators (Montgomery's trick), then local prefix products
+        // Z[i+1] = Z[tile start] * prod_{j<=i} num_j / prod_{j<=i} den_j.  No per-row (or per-thread) inversion:
+        // 1 / prod_{j<=i} den_j = (prod_{j>i} den_j) / (prod of all den of the tile), so one forward scan of the
+        // numerators, one backward scan of the denominators and ONE inversion per tile do it.
         const uint32_t cnt = hi - lo;
-        fr_t pre[GP_PER];
-        fr_t acc = fe_one<FR>();
-        for (uint32_t k = 0; k < cnt; k++) { pre[k] = acc; acc = mul(acc, den[k]); }
-        fr_t iacc = inv(acc);
-        for (uint32_t k = cnt; k-- > 0;) {
-            fr_t dinv = mul(iacc, pre[k]);
-            iacc = mul(iacc, den[k]);
-            num[k] = mul(num[k], dinv);              // ratio_k
-        }
-        acc = fe_one<FR>();
-        for (uint32_t k = 0; k < cnt; k++) { acc = mul(acc, num[k]); num[k] = acc; }   // inclusive local products
-        fe_store(&S[tid], acc);
+        fr_t tn = fe_one<FR>(), td = fe_one<FR>();
+        for (uint32_t k = 0; k < cnt; k++) { tn = mul(tn, num[k]); num[k] = tn; }            // inclusive local prefix of num
+        for (uint32_t k = cnt; k-- > 0;) { const fr_t d = den[k]; den[k] = td; td = mul(td, d); }   // exclusive local suffix of den
+        fr_t* SN = S;                                  // [2][GP_THREADS] numerators: prefix over threads
+        fr_t* SD = S + 2 * GP_THREADS;                 // [2][GP_THREADS] denominators: suffix over threads
+        fe_store(&SN[tid], tn);
+        fe_store(&SD[tid], td);
         __syncthreads();
         int cur = 0;
         for (uint32_t d = 1; d < GP_THREADS; d <<= 1) {
-            fr_t v = fe_load(&S[cur * GP_THREADS + tid]);
-            if (tid >= d) v = mul(v, fe_load(&S[cur * GP_THREADS + tid - d]));
-            fe_store(&S[(cur ^ 1) * GP_THREADS + tid], v);
+            fr_t vn = fe_load(&SN[cur * GP_THREADS + tid]);
+            fr_t vd = fe_load(&SD[cur * GP_THREADS + tid]);
+            if (tid >= d) vn = mul(vn, fe_load(&SN[cur * GP_THREADS + tid - d]));
+            if (tid + d < GP_THREADS) vd = mul(vd, fe_load(&SD[cur * GP_THREADS + tid + d]));
+            fe_store(&SN[(cur ^ 1) * GP_THREADS + tid], vn);
+            fe_store(&SD[(cur ^ 1) * GP_THREADS + tid], vd);
             cur ^= 1;
             __syncthreads();
         }
+        // SN[t] = prod of the numerators of threads <= t, SD[t] = prod of the denominators of threads >= t
+        if (tid == 0) fe_store(&tile_inv, inv(fe_load(&SD[cur * GP_THREADS])));
+        __syncthreads();
         const fr_t tc = fe_load(&tile_carry);
-        fr_t carry = tid ? mul(tc, fe_load(&S[cur * GP_THREADS + tid - 1])) : tc;
-        for (uint32_t k = 0; k < cnt; k++) fe_store(Z + lo + k + 1, mul(carry, num[k]));
-        __syncthreads();                             // everyone has read tile_carry and S
-        if (tid == GP_THREADS - 1) fe_store(&tile_carry, mul(tc, fe_load(&S[cur * GP_THREADS + tid])));
+        fr_t common = mul(tc, fe_load(&tile_inv));
+        if (tid) common = mul(common, fe_load(&SN[cur * GP_THREADS + tid - 1]));
+        if (tid + 1 < GP_THREADS) common = mul(common, fe_load(&SD[cur * GP_THREADS + tid + 1]));
+        for (uint32_t k = 0; k < cnt; k++) fe_store(Z + lo + k + 1, mul(common, mul(num[k], den[k])));
+        __syncthreads();                             // everyone has read tile_carry, tile_inv and the scans
+        if (tid == GP_THREADS - 1) fe_store(&tile_carry, mul(mul(tc, fe_load(&tile_inv)), fe_load(&SN[cur * GP_THREADS + tid])));
         __syncthreads();
     }
     // blinding rows
@@ -402,12 +408,21 @@ __global__ void __launch_bounds__(256) k_eval(const EvalTask* tasks, const fr_t*
     if (threadIdx.x == 0) fe_store(out + blockIdx.x, fe_load(&red[0]));
 }
 // out[row] = sum_j coef[j] * polys[j][row]
-__global__ void k_lincomb(const fr_t* const* polys, const fr_t* coef, uint32_t m, uint32_t n, fr_t* out) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
+// out[row] = sum_j coef[j] * polys[j][row].  A block is 32 rows x LC_SPLIT slices of the polynomial list (the list has
+// up to ~470 entries and there are only n rows: one thread per row left the GPU almost empty).
+static constexpr uint32_t LC_SPLIT = 8;
+__global__ void __launch_bounds__(32 * LC_SPLIT) k_lincomb(const fr_t* const* polys, const fr_t* coef, uint32_t m, uint32_t n, fr_t* out) {
+    __shared__ fr_t part[LC_SPLIT][32];
+    const uint32_t row = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
     fr_t acc = fe_zero<FR>();
-    for (uint32_t j = 0; j < m; j++) acc = add(acc, mul(fe_load(coef + j), fe_load(polys[j] + row)));
-    fe_store(out + row, acc);
+    if (row < n)
+        for (uint32_t j = y; j < m; j += LC_SPLIT) acc = add(acc, mul(fe_load(coef + j), fe_load(polys[j] + row)));
+    fe_store(&part[y][threadIdx.x], acc);
+    __syncthreads();
+    if (y == 0 && row < n) {
+        for (uint32_t k = 1; k < LC_SPLIT; k++) acc = add(acc, fe_load(&part[k][threadIdx.x]));
+        fe_store(out + row, acc);
+    }
 }
 // SHPLONK quotient on the coset zeta*H: acc[row] += scale * (f[row] - r(c)) / Z(c), c = zeta * w^row.
 // r and Z are given by their coefficients (degree <= 3 and <= 4).
@@ -703,7 +718,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         g.ap_base = pr->ap_base; g.lookup_adv_base = pr->lookup_adv_base; g.fixed_lagrange = pk->fixed_lagrange;
         g.fx_table = pk->fx_table; g.fx_const = pk->fx_const; g.fx_sigma = pk->fx_sigma; g.inst = pr->inst;
         g.delta_pow = pk->delta_pow; g.tw = dom->tw_fwd; g.blind = pr->blind; g.beta = dev(pr->beta); g.gamma = dev(pr->gamma);
-        const size_t smem = 2 * GP_THREADS * sizeof(fr_t);
+        const size_t smem = 4 * GP_THREADS * sizeof(fr_t);
         ZK_CUDA(ctx, cudaFuncSetAttribute(k_grand_product, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_grand_product<<<nz, GP_THREADS, smem, ctx->stream>>>(g);
         ZK_CHECK_LAUNCH(ctx);
@@ -902,7 +917,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
             }
             ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs + set_off[s], set_polys[s].data(), set_polys[s].size() * 8, cudaMemcpyHostToDevice, ctx->stream));
             ZK_CUDA(ctx, cudaMemcpyAsync(d_coef + set_off[s], set_coef[s].data(), set_coef[s].size() * 32, cudaMemcpyHostToDevice, ctx->stream));
-            k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs + set_off[s], d_coef + set_off[s], (uint32_t)set_polys[s].size(), n,
+            k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs + set_off[s], d_coef + set_off[s], (uint32_t)set_polys[s].size(), n,
                                                                 fbuf + (size_t)s * n);
             ZK_CHECK_LAUNCH(ctx);
         }
@@ -939,7 +954,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         lc.push_back(host::neg(zt));
         ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         ZK_CUDA(ctx, cudaMemcpyAsync(d_coef, lc.data(), lc.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
-        k_lincomb<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)lp.size(), n, Lp);
+        k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)lp.size(), n, Lp);
         ZK_CHECK_LAUNCH(ctx);
         k_sub_const0<<<1, 1, 0, ctx->stream>>>(Lp, dev(cst));
         ZK_CHECK_LAUNCH(ctx);
