@@ -173,31 +173,10 @@ def cpu_reference_arm(steps, warmup, threads=0):
 def synth_inputs(ctx, rng, count):
     """SURVEY.md §8(d) synthetic BFV witnesses for config 1: u uniform on {0,1,Q-1}, e0/e1 rounded
     N(0,3.2^2) clipped to +-B, m uniform on [-T/2,T/2], pk0/pk1 uniform; c0, c1 computed with the
-    library's own device-resident Poly arithmetic (Poly::mul / reduce / divide_by_cyclo)."""
-    from zk_fhe_b200.poly import Poly
-    N, Q, T, B = N_POLY, Q_MOD, T_MOD, B_ERR
-    out = []
-    cyclo = [1] + [0] * (N - 1) + [1]
-    for _ in range(count):
-        pk0 = rng.integers(0, Q, N).tolist()
-        pk1 = rng.integers(0, Q, N).tolist()
-        u = (rng.integers(0, 3, N) * 1).tolist()
-        u = [Q - 1 if x == 2 else x for x in u]
-        e0 = (np.clip(np.rint(rng.normal(0, 3.2, N)), -B, B).astype(np.int64) % Q).tolist()
-        e1 = (np.clip(np.rint(rng.normal(0, 3.2, N)), -B, B).astype(np.int64) % Q).tolist()
-        m = (rng.integers(-(T // 2), T // 2 + 1, N) % Q).tolist()
-        pu, pc = Poly.from_string(ctx, [str(x) for x in u], Q), Poly.from_string(ctx, [str(x) for x in cyclo], Q)
-        rems = []
-        for pk in (pk0, pk1):
-            red = Poly.from_string(ctx, [str(x) for x in pk], Q).mul(pu).reduce_by_modulus(Q)
-            _, rem = red.divide_by_cyclo(pc, Q)
-            rems.append(rem.coefficients[-N:])
-        delta = Q // T
-        c0 = [(r + delta * mi + ei) % Q for r, mi, ei in zip(rems[0], m, e0)]
-        c1 = [(r + ei) % Q for r, ei in zip(rems[1], e1)]
-        d = dict(pk0=pk0, pk1=pk1, m=m, u=u, e0=e0, e1=e1, c0=c0, c1=c1, cyclo=cyclo)
-        out.append({k: [str(x) for x in v] for k, v in d.items()})
-    return out
+    library's own device-resident Poly arithmetic (the package's witness front-end, bfv_py)."""
+    from zk_fhe_b200 import bfv, bfv_py
+    params = bfv.BfvParams(N=N_POLY, Q=Q_MOD, T=T_MOD, B=B_ERR)
+    return [bfv_py.keygen_and_encrypt(ctx, params, rng, with_secret_key=False) for _ in range(count)]
 
 
 def main():
