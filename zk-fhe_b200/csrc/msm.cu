@@ -29,7 +29,8 @@ namespace zkfhe {
 
 // point references summed by one accumulate thread: long slices for big batches (fewer partial sums),
 // short ones when only a few columns are committed (shorter dependent chain, more threads)
-static inline uint32_t pick_seg(uint32_t batch) { return batch < 32 ? 16 : 64; }
+// (small-valued columns have a few references per scalar: short slices keep enough threads in flight)
+static inline uint32_t pick_seg(uint32_t batch, bool narrow) { return batch < 32 || narrow ? 16 : 64; }
 
 // ---- fixed-base table ---------------------------------------------------------------------
 __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint32_t n, uint32_t c, uint32_t W) {
@@ -286,6 +287,61 @@ __global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uin
     xyzz_store(o + 1, acc);
 }
 
+// Reduction, level 1, latency variant for commits of a few columns (the h pieces, the two SHPLONK quotients, the
+// phase-0 advice): one WARP per group of 32 buckets, lane = bucket.  The running sums become a shuffle suffix scan
+// (R_l = sum_{m >= l} B_m, so S_g = R_0 and A_g = sum_l R_l by a shuffle tree): ~12 dependent point additions
+// instead of 2 * 16 + the partial lists, at 5x the arithmetic -- irrelevant when the GPU is otherwise empty, wrong
+// for the 100+ column commits, which stay on k_msm_fold.
+__device__ __forceinline__ g1_xyzz xyzz_shfl_down_w(const g1_xyzz& p, uint32_t d) {
+    g1_xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+        r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+        r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
+        r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(128) k_msm_fold_warp(uint32_t c, uint32_t SEG1, const uint32_t* __restrict__ bucket_off,
+                                                       const uint32_t* __restrict__ rank_in,
+                                                       const g1_xyzz* __restrict__ partial1, uint64_t partial1_stride,
+                                                       const g1_xyzz* __restrict__ partial2, uint64_t partial2_stride,
+                                                       const uint32_t* __restrict__ skew,
+                                                       g1_xyzz* group_out /* [col][NB/32][2] */) {
+    const uint32_t NB = 1u << (c - 1), groups = NB >> 5;
+    const uint32_t col = blockIdx.y, lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= groups) return;                              // whole warps only: blockDim is a multiple of 32
+    const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
+    const bool sk = skew[col] != 0;
+    const uint32_t SEG = sk ? SEG1 * SUP : SEG1;
+    const g1_xyzz* part = sk ? partial2 + (uint64_t)col * partial2_stride : partial1 + (uint64_t)col * partial1_stride;
+    const uint32_t b = (g << 5) + lane;
+    g1_xyzz R = xyzz_identity();
+    const uint32_t e0 = boff[b], e1 = boff[b + 1];
+    if (e1 > e0) {
+        const uint32_t r = rnk[b];
+        for (uint32_t t = e0 / SEG; t <= (e1 - 1) / SEG; t++) xyzz_add_ni(R, xyzz_load(part + r + t));
+    }
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {               // R_l = sum_{m >= l} B_m
+        g1_xyzz v = xyzz_shfl_down_w(R, d);
+        if (lane + d < 32) xyzz_add_ni(R, v);
+    }
+    g1_xyzz A = R;
+#pragma unroll 1
+    for (uint32_t d = 16; d > 0; d >>= 1) {               // A_g = sum_l R_l
+        g1_xyzz v = xyzz_shfl_down_w(A, d);
+        if (lane < d) xyzz_add_ni(A, v);
+    }
+    if (lane == 0) {
+        g1_xyzz* o = group_out + ((size_t)col * groups + g) * 2;
+        xyzz_store(o, R);
+        xyzz_store(o + 1, A);
+    }
+}
+
 // Reduction, level 2: ONE WARP per column, lane l owning `per` consecutive groups.
 //   total = sum_g A_g + fold * sum_g g * S_g
 // Inside a lane (g0 = l * per): S_l = sum S_g, W_l = sum (g - g0) S_g (running sums), A_l = sum A_g.
@@ -456,7 +512,7 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     const g1_affine* table = narrow ? B.table_s : B.table;
     const uint32_t n = 1u << log_n, c = narrow ? B.c_s : B.c, W = narrow ? B.W_s : B.W, NB = 1u << (c - 1);
     const uint64_t max_refs = (uint64_t)n * W;
-    const uint32_t SEG = pick_seg(batch);
+    const uint32_t SEG = pick_seg(batch, narrow);
     const uint64_t max_thr = (max_refs + SEG - 1) / SEG;     // accumulate threads per column
     const uint64_t max_segs = NB + max_thr;                  // partial slots: rank[b] + t
     // bound the workspace: process the batch in chunks
@@ -482,6 +538,8 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     uint32_t log_fold = 4;
     while (log_fold && (NB >> log_fold) == 0) log_fold--;
     while ((NB >> log_fold) > 512u) log_fold++;
+    const bool warp_fold = batch < 32 && NB >= 1024 && (NB >> 5) <= 512u;     // few columns: the latency variant
+    if (warp_fold) log_fold = 5;
     const uint32_t groups = NB >> log_fold;
     g1_xyzz* grp;
     ZK_TRY(ws_get(ctx, "msm_groups", (size_t)chunk * groups * 2 * sizeof(g1_xyzz), (void**)&grp));
@@ -512,8 +570,13 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         dim3 cgrid((uint32_t)((max_segs2 + 127) / 128), nb);
         k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew);
         ZK_CHECK_LAUNCH(ctx);
-        dim3 fgrid((groups + 127) / 128, nb);
-        k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
+        if (warp_fold) {
+            dim3 fgrid((groups * 32 + 127) / 128, nb);
+            k_msm_fold_warp<<<fgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
+        } else {
+            dim3 fgrid((groups + 127) / 128, nb);
+            k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
+        }
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
