@@ -123,6 +123,10 @@ int zkfhe_msm_g1_dev_ex(zkfhe_ctx* ctx, const uint8_t* d_scalars, uint32_t batch
 typedef struct zkfhe_poly zkfhe_poly;
 /* Poly::from_string after decimal parsing (poly.rs:21-40): asserts coeff <= modulus (:28). */
 int zkfhe_poly_from_u64(zkfhe_ctx* ctx, const uint64_t* h_coeffs, uint32_t len, uint64_t modulus, zkfhe_poly** out);
+/* Poly::from_string including the decimal parsing (poly.rs:21-40): `text` holds `len` non-negative decimal
+ * integers separated by single commas (no spaces); a malformed number is ZKFHE_ERR_ARG, as the reference's
+ * `parse().unwrap()` panics (:25). */
+int zkfhe_poly_from_decimal(zkfhe_ctx* ctx, const char* text, size_t text_len, uint32_t len, uint64_t modulus, zkfhe_poly** out);
 /* Poly::from_big_int (poly.rs:47-59): asserts bits(coeff) <= max_bits (:51). */
 int zkfhe_poly_from_u256(zkfhe_ctx* ctx, const uint64_t* h_coeffs_u256, uint32_t len, uint64_t max_bits, zkfhe_poly** out);
 /* Poly::mul (poly.rs:75-103): exact integer product of two equal-degree polynomials, computed

@@ -73,6 +73,20 @@ def test_ntt_edge_inputs(ctx):
     ctx.ntt_fr(np.zeros((0, 4), np.uint64), k, 0)          # empty batch is a no-op
 
 
+def test_ntt_2_pow_21_matches_oracle(ctx):
+    """The extended domain of config 5 (k = 19 -> 2^21 points): the largest transform the prover issues."""
+    k = 21
+    rng = np.random.default_rng(21)
+    data = random_fr_mont(rng, 1 << k)
+    want = data.copy()
+    cbind.ntt(want, k, 1, coset=True)
+    ctx.ntt_fr(data, k, 1, coset=True)
+    assert np.array_equal(data, want)
+    ctx.ntt_fr(data, k, 1, inverse=True, coset=True)
+    cbind.ntt(want, k, 1, inverse=True, coset=True)
+    assert np.array_equal(data, want)
+
+
 @pytest.mark.parametrize("k", [13, 16, 19])
 def test_ntt_full_size_roundtrip_and_linearity(ctx, k):
     """BASELINE.json sizes (k = 13, 16, 19): iNTT(NTT(x)) == x, coset round trip, linearity."""

@@ -77,6 +77,14 @@ def test_poly_error_behaviour_matches_reference_asserts(ctx):
     ctx.status()                                            # cleared after being reported
     assert Poly.from_string(ctx, ["7", "0"], 7).coefficients == [7, 0]     # `<=`, not `<`
     ctx.status()
+    # the decimal parser (poly.rs:25 `parse().unwrap()`): malformed numbers, signs, blanks and > u64 are errors
+    for bad in (["12", "x3"], ["-1", "2"], ["1", ""], ["1 ", "2"], ["18446744073709551616", "1"], ["1,2", "3"]):
+        with pytest.raises(E) as e:
+            Poly.from_string(ctx, bad, 7)
+        assert e.value.code == -2, bad
+    big = Poly.from_string(ctx, ["18446744073709551615", "0", "00042"], (1 << 64) - 1)
+    assert big.coefficients == [18446744073709551615, 0, 42]
+    ctx.status()
     with pytest.raises(E) as e:                             # equal degrees required (poly.rs:78)
         Poly.from_string(ctx, ["1", "2"], 7).mul(Poly.from_string(ctx, ["1", "2", "3"], 7))
     assert e.value.code == -4

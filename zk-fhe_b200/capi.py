@@ -68,6 +68,7 @@ _SIGNATURES = {
                                     _c.POINTER(_c.c_uint64)]),
     # stage (1a): Poly
     "zkfhe_poly_from_u64": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    "zkfhe_poly_from_decimal": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
     "zkfhe_poly_from_u256": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
     "zkfhe_poly_mul": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p)]),
     "zkfhe_poly_reduce_by_modulus": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.POINTER(_c.c_void_p)]),

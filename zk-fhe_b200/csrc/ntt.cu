@@ -277,6 +277,7 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         if (const char* e = getenv("ZKFHE_NTT_LOG_T")) log_t = (uint32_t)atoi(e);      // tuning knob (tools/bench_kernels.py)
         if (log_t < 10) log_t = 10;
         if (log_t > 12) log_t = 12;
+        if (log_t < (log_n + 1) / 2) log_t = (log_n + 1) / 2;          // a tile holds at least one whole pass-A column
         const uint32_t log_ra = (log_n + 1) / 2, log_c = log_n - log_ra;
         fr_t* tmp;
         ZK_TRY(ws_get(ctx, "ntt_tmp", ((size_t)batch << log_n) * sizeof(fr_t), (void**)&tmp));

@@ -518,6 +518,35 @@ int zkfhe_poly_from_u64(zkfhe_ctx* ctx, const uint64_t* h_coeffs, uint32_t len, 
     return ZKFHE_OK;
 }
 
+// Poly::from_string itself (poly.rs:21-40): `len` decimal integers separated by single commas.  Parsing 9 x 1024
+// strings per proof in the host language of the caller costs more than the transfer; here it is one pass in C.
+int zkfhe_poly_from_decimal(zkfhe_ctx* ctx, const char* text, size_t text_len, uint32_t len, uint64_t modulus, zkfhe_poly** out) {
+    if (!ctx || !out || !text) return fail(ctx, ZKFHE_ERR_ARG, "poly_from_decimal: null pointer");
+    std::vector<uint64_t> vals;
+    vals.reserve(len);
+    size_t i = 0;
+    while (i < text_len) {
+        uint64_t v = 0;
+        size_t digits = 0;
+        while (i < text_len && text[i] >= '0' && text[i] <= '9') {
+            const uint64_t d = (uint64_t)(text[i] - '0');
+            if (v > (UINT64_MAX - d) / 10) return fail(ctx, ZKFHE_ERR_ARG, "coefficient does not fit u64 (the reference modulus is u64)");
+            v = v * 10 + d;
+            digits++;
+            i++;
+        }
+        if (!digits) return fail(ctx, ZKFHE_ERR_ARG, "poly_from_decimal: invalid digit found in string (src/poly.rs:25) at offset %zu", i);
+        vals.push_back(v);
+        if (i < text_len) {
+            if (text[i] != ',') return fail(ctx, ZKFHE_ERR_ARG, "poly_from_decimal: invalid digit found in string (src/poly.rs:25) at offset %zu", i);
+            i++;
+            if (i == text_len) return fail(ctx, ZKFHE_ERR_ARG, "poly_from_decimal: trailing separator");
+        }
+    }
+    if (vals.size() != len) return fail(ctx, ZKFHE_ERR_ARG, "poly_from_decimal: %zu coefficients, expected %u", vals.size(), len);
+    return zkfhe_poly_from_u64(ctx, vals.data(), len, modulus, out);
+}
+
 int zkfhe_poly_from_u256(zkfhe_ctx* ctx, const uint64_t* h, uint32_t len, uint64_t max_bits, zkfhe_poly** out) {
     if (!ctx || !out || (!h && len)) return fail(ctx, ZKFHE_ERR_ARG, "poly_from_u256: null pointer");
     if (len == 0) return fail(ctx, ZKFHE_ERR_ASSERT, "attempt to subtract with overflow: coefficients.len() - 1 (src/poly.rs:48)");

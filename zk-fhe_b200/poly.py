@@ -29,15 +29,12 @@ class Poly:
     @classmethod
     def from_string(cls, ctx, coefficients, modulus):
         """Poly::from_string (poly.rs:21-40): decimal strings, each <= modulus."""
-        vals = []
-        for s in coefficients:
-            v = int(s, 10)
-            if v < 0 or v >= 1 << 64:
-                raise ZkfheError(-2, "coefficient does not fit u64 (the reference modulus is u64)")
-            vals.append(v)
-        arr = np.array(vals, dtype=np.uint64)
+        try:
+            text = ",".join(coefficients).encode("ascii")      # parsed in C: one pass instead of len(coefficients) int() calls
+        except (TypeError, UnicodeEncodeError):
+            raise ZkfheError(-2, "coefficients must be decimal strings")
         h = ctypes.c_void_p()
-        ctx._check(ctx.lib.zkfhe_poly_from_u64(ctx.h, _addr(arr), len(vals), modulus, ctypes.byref(h)))
+        ctx._check(ctx.lib.zkfhe_poly_from_decimal(ctx.h, text, len(text), len(coefficients), modulus, ctypes.byref(h)))
         return cls(ctx, h)
 
     @classmethod
