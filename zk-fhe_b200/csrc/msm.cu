@@ -23,7 +23,11 @@
 //    shared-memory tree reduction and a single inversion give the affine point.
 //  * The hot loop (2) gathers 64-byte affine points from the L2-resident table;
 //    scalars are read once, coalesced.
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace zkfhe {
 
@@ -162,6 +166,121 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     __syncthreads();
 
     for (uint32_t i = tid; i < n; i += nt) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
+            uint32_t pos = atomicAdd(&cnt[b], 1u);
+            out[pos] = (w * n + i) | (negative ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// The same counting sort spread over a thread-block CLUSTER of SORT_CS CTAs per column (distributed shared memory):
+// CTA q histograms scalars [q n/CS, (q+1) n/CS) into its own shared memory; after a cluster barrier it owns the
+// bucket slice [q NB/CS, (q+1) NB/CS), reads the CS histograms of those buckets through DSMEM, scans them, and writes
+// back -- into every CTA's shared memory -- that CTA's first output position inside each bucket; a second barrier,
+// and every CTA scatters its own scalars with shared-memory cursors.  One CTA per column is the right shape when a
+// commit phase has 100+ columns of 2^13; a 1-3 column commit, or columns of 2^16..2^19 scalars, left 140 SMs idle for
+// the whole sort (74 of 480 ms at k = 19).
+static constexpr uint32_t SORT_CS = 8;
+__global__ void __cluster_dims__(SORT_CS, 1, 1) __launch_bounds__(1024)
+k_msm_sort_cluster(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c, uint32_t W, uint32_t* bucket_off,
+                   uint32_t* rank_out, uint32_t* sorted, uint64_t sorted_stride, uint32_t skew_limit, uint32_t* skew_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t NB = 1u << (c - 1);
+    uint32_t* cnt = msm_smem;                 // [NB] this CTA's histogram, then its scatter cursors
+    __shared__ uint32_t warp_tot[2][32];
+    __shared__ uint32_t blk_tot[3];
+    __shared__ uint32_t slice_sum[SORT_CS][3];                // (references, non-empty buckets, skewed) per bucket slice
+    const uint32_t q = cluster.block_rank(), col = blockIdx.x / SORT_CS, tid = threadIdx.x, nt = blockDim.x;
+    const fr_t* sc = scalars + (uint64_t)col * stride;
+    uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
+    uint32_t* rnk = rank_out + (size_t)col * (NB + 1);
+    uint32_t* out = sorted + (uint64_t)col * sorted_stride;
+    const uint32_t i0 = (uint32_t)((uint64_t)n * q / SORT_CS), i1 = (uint32_t)((uint64_t)n * (q + 1) / SORT_CS);
+
+    for (uint32_t b = tid; b < NB; b += nt) cnt[b] = 0;
+    __syncthreads();
+    for (uint32_t i = i0 + tid; i < i1; i += nt) {
+        fr_t s = from_mont(fe_load(sc + i));
+        for_each_digit(s, c, W, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
+    }
+    cluster.sync();
+
+    // bucket slice of this CTA: totals over the CS histograms, exclusive scans inside the slice
+    uint32_t* rc[SORT_CS];
+#pragma unroll
+    for (uint32_t r = 0; r < SORT_CS; r++) rc[r] = cluster.map_shared_rank(cnt, r);
+    const uint32_t slice = NB / SORT_CS, b_lo = q * slice, b_hi = b_lo + slice;
+    const uint32_t per = (slice + nt - 1) / nt;
+    const uint32_t b0 = b_lo + tid * per;
+    uint32_t sum_e = 0, sum_s = 0, max_c = 0;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t b = b0 + k;
+        if (b < b_hi) {
+            uint32_t v = 0;
+#pragma unroll
+            for (uint32_t r = 0; r < SORT_CS; r++) v += rc[r][b];
+            sum_e += v; sum_s += (v != 0); max_c = max(max_c, v);
+        }
+    }
+    const uint32_t any_skew = __syncthreads_or(max_c > skew_limit);
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+    uint32_t inc_e = sum_e, inc_s = sum_s;
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t te = __shfl_up_sync(0xffffffffu, inc_e, d);
+        uint32_t ts = __shfl_up_sync(0xffffffffu, inc_s, d);
+        if (lane >= d) { inc_e += te; inc_s += ts; }
+    }
+    if (lane == 31) { warp_tot[0][wid] = inc_e; warp_tot[1][wid] = inc_s; }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t nw = (nt + 31) / 32;
+        uint32_t ve = lane < nw ? warp_tot[0][lane] : 0, vs = lane < nw ? warp_tot[1][lane] : 0;
+        uint32_t ie = ve, is = vs;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            uint32_t te = __shfl_up_sync(0xffffffffu, ie, d);
+            uint32_t ts = __shfl_up_sync(0xffffffffu, is, d);
+            if (lane >= d) { ie += te; is += ts; }
+        }
+        warp_tot[0][lane] = ie - ve;   // exclusive warp offsets
+        warp_tot[1][lane] = is - vs;
+        if (lane == 31) { blk_tot[0] = ie; blk_tot[1] = is; blk_tot[2] = any_skew; }
+    }
+    __syncthreads();
+    if (tid < SORT_CS) {                                        // publish this slice's totals to every CTA of the cluster
+        uint32_t* ss = cluster.map_shared_rank(&slice_sum[0][0], tid);
+        ss[q * 3 + 0] = blk_tot[0];
+        ss[q * 3 + 1] = blk_tot[1];
+        ss[q * 3 + 2] = blk_tot[2];
+    }
+    cluster.sync();
+    uint32_t base_e = 0, base_s = 0, skewed = 0, all_e = 0, all_s = 0;
+    for (uint32_t r = 0; r < SORT_CS; r++) {
+        if (r < q) { base_e += slice_sum[r][0]; base_s += slice_sum[r][1]; }
+        all_e += slice_sum[r][0]; all_s += slice_sum[r][1]; skewed |= slice_sum[r][2];
+    }
+    uint32_t run_e = base_e + warp_tot[0][wid] + inc_e - sum_e;
+    uint32_t run_s = base_s + warp_tot[1][wid] + inc_s - sum_s;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t b = b0 + k;
+        if (b < b_hi) {
+            boff[b] = run_e;
+            rnk[b] = run_s;
+            uint32_t pos = run_e;
+#pragma unroll
+            for (uint32_t r = 0; r < SORT_CS; r++) {            // CTA r's first position inside bucket b
+                const uint32_t h = rc[r][b];
+                rc[r][b] = pos;
+                pos += h;
+            }
+            run_s += (pos != run_e);
+            run_e = pos;
+        }
+    }
+    if (q == 0 && tid == 0) { boff[NB] = all_e; rnk[NB] = all_s; skew_out[col] = skewed ? 1u : 0u; }
+    cluster.sync();                                             // every cursor is in place (and no DSMEM access after this)
+
+    for (uint32_t i = i0 + tid; i < i1; i += nt) {
         fr_t s = from_mont(fe_load(sc + i));
         for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
             uint32_t pos = atomicAdd(&cnt[b], 1u);
@@ -553,12 +672,19 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         if (fresh) ZK_CUDA(ctx, cudaMemsetAsync(refs, 0, 8, ctx->stream));
     }
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_sort_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    // a cluster of 8 CTAs per column when there are few columns or they are long; one CTA per column otherwise
+    bool cluster_sort = log_n >= 13 && NB >= 8 * SORT_CS && (batch < 32 || log_n >= 15);
+    if (const char* e = getenv("ZKFHE_MSM_CLUSTER_SORT")) cluster_sort = cluster_sort && atoi(e) != 0;
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
         const fr_t* sc = d_scalars + (uint64_t)done * stride;
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
-        k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
+        if (cluster_sort)
+            k_msm_sort_cluster<<<nb * SORT_CS, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
+        else
+            k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
