@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) k_msm_combine(uint32_t c, uint32_t SEG, c
 // Reduction, level 1: one thread per group of FOLD consecutive buckets.  Folds the partial sums of
 // each bucket and runs the running-sum trick inside the group:
 //   S_g = sum_b B_b,   A_g = sum_b (b - lo + 1) B_b      (so sum_b (b+1) B_b = A_g + lo * S_g)
-__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uint32_t SEG1, const uint32_t* __restrict__ bucket_off,
+__global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uint32_t SEG1, uint32_t SEG2, const uint32_t* __restrict__ bucket_off,
                                                   const uint32_t* __restrict__ rank_in,
                                                   const g1_xyzz* __restrict__ partial1, uint64_t partial1_stride,
                                                   const g1_xyzz* __restrict__ partial2, uint64_t partial2_stride,
@@ -387,9 +387,10 @@ __global__ void __launch_bounds__(128) k_msm_fold(uint32_t c, uint32_t fold, uin
     if (g >= groups) return;
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
     const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
-    // skewed columns were combined SUP slices at a time (level 2); the others are read at level 1
+    // skewed columns were combined SUP slices at a time, one or more times (SEG2 references per slot); the others
+    // are read at level 1 (SEG1 references per slot)
     const bool sk = skew[col] != 0;
-    const uint32_t SEG = sk ? SEG1 * SUP : SEG1;
+    const uint32_t SEG = sk ? SEG2 : SEG1;
     const g1_xyzz* part = sk ? partial2 + (uint64_t)col * partial2_stride : partial1 + (uint64_t)col * partial1_stride;
     const uint32_t lo = g * fold;
     g1_xyzz running = xyzz_identity(), acc = xyzz_identity();
@@ -422,7 +423,7 @@ __device__ __forceinline__ g1_xyzz xyzz_shfl_down_w(const g1_xyzz& p, uint32_t d
     }
     return r;
 }
-__global__ void __launch_bounds__(128) k_msm_fold_warp(uint32_t c, uint32_t SEG1, const uint32_t* __restrict__ bucket_off,
+__global__ void __launch_bounds__(128) k_msm_fold_warp(uint32_t c, uint32_t SEG1, uint32_t SEG2, const uint32_t* __restrict__ bucket_off,
                                                        const uint32_t* __restrict__ rank_in,
                                                        const g1_xyzz* __restrict__ partial1, uint64_t partial1_stride,
                                                        const g1_xyzz* __restrict__ partial2, uint64_t partial2_stride,
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(128) k_msm_fold_warp(uint32_t c, uint32_t SEG1
     const uint32_t* boff = bucket_off + (size_t)col * (NB + 1);
     const uint32_t* rnk = rank_in + (size_t)col * (NB + 1);
     const bool sk = skew[col] != 0;
-    const uint32_t SEG = sk ? SEG1 * SUP : SEG1;
+    const uint32_t SEG = sk ? SEG2 : SEG1;
     const g1_xyzz* part = sk ? partial2 + (uint64_t)col * partial2_stride : partial1 + (uint64_t)col * partial1_stride;
     const uint32_t b = (g << 5) + lane;
     g1_xyzz R = xyzz_identity();
@@ -646,9 +647,23 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     ZK_TRY(ws_get(ctx, "msm_soff", (size_t)chunk * (NB + 1) * 4, (void**)&soff));
     ZK_TRY(ws_get(ctx, "msm_sorted", (size_t)chunk * max_refs * 4, (void**)&sorted));
     ZK_TRY(ws_get(ctx, "msm_partial", (size_t)chunk * max_segs * sizeof(g1_xyzz), (void**)&partial));
-    const uint64_t max_segs2 = NB + (max_thr + SUP - 1) / SUP + 1;      // level-2 slots: rank[b] + super-slice
-    g1_xyzz* partial2;
-    ZK_TRY(ws_get(ctx, "msm_partial2", (size_t)chunk * max_segs2 * sizeof(g1_xyzz), (void**)&partial2));
+    // combine levels for skewed columns: level l has one slot per (bucket, run of SEG * SUP^l references); enough
+    // levels that even a bucket holding one reference per scalar ends with <= 32 partial sums for the fold chain
+    // (one level at k = 13; a single level left 2048-long chains on the 0/1-valued witness columns at k = 19)
+    uint32_t levels = 1;
+    uint64_t seg_top = (uint64_t)SEG * SUP;
+    while (levels < 3 && n / seg_top > 32) { levels++; seg_top *= SUP; }
+    uint64_t lvl_slots[4] = {max_segs, 0, 0, 0};
+    g1_xyzz* lvl_buf[4] = {partial, nullptr, nullptr, nullptr};
+    {
+        static const char* names[4] = {"", "msm_partial2", "msm_partial3", "msm_partial4"};
+        uint64_t div = 1;
+        for (uint32_t l = 1; l <= levels; l++) {
+            div *= SUP;
+            lvl_slots[l] = NB + (max_thr + div - 1) / div + 1;
+            ZK_TRY(ws_get(ctx, names[l], (size_t)chunk * lvl_slots[l] * sizeof(g1_xyzz), (void**)&lvl_buf[l]));
+        }
+    }
     uint32_t* skew;
     ZK_TRY(ws_get(ctx, "msm_skew", (size_t)chunk * 4, (void**)&skew));
     // reduction shape: groups of 2^log_fold buckets; the final warp owns groups/32 groups per lane.
@@ -693,15 +708,21 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FOLD, 0));
-        dim3 cgrid((uint32_t)((max_segs2 + 127) / 128), nb);
-        k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew);
-        ZK_CHECK_LAUNCH(ctx);
+        {
+            uint32_t seg_in = SEG;
+            for (uint32_t l = 1; l <= levels; l++) {
+                dim3 cgrid((uint32_t)((lvl_slots[l] + 127) / 128), nb);
+                k_msm_combine<<<cgrid, 128, 0, ctx->stream>>>(c, seg_in, boff, soff, lvl_buf[l - 1], lvl_slots[l - 1], lvl_buf[l], lvl_slots[l], skew);
+                ZK_CHECK_LAUNCH(ctx);
+                seg_in *= SUP;
+            }
+        }
         if (warp_fold) {
             dim3 fgrid((groups * 32 + 127) / 128, nb);
-            k_msm_fold_warp<<<fgrid, 128, 0, ctx->stream>>>(c, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
+            k_msm_fold_warp<<<fgrid, 128, 0, ctx->stream>>>(c, SEG, (uint32_t)seg_top, boff, soff, partial, max_segs, lvl_buf[levels], lvl_slots[levels], skew, grp);
         } else {
             dim3 fgrid((groups + 127) / 128, nb);
-            k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG, boff, soff, partial, max_segs, partial2, max_segs2, skew, grp);
+            k_msm_fold<<<fgrid, 128, 0, ctx->stream>>>(c, 1u << log_fold, SEG, (uint32_t)seg_top, boff, soff, partial, max_segs, lvl_buf[levels], lvl_slots[levels], skew, grp);
         }
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
