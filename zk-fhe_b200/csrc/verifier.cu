@@ -208,21 +208,21 @@ int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t
         const Fr x = tr.squeeze();
 
         // ---- opening table, in the prover's order ------------------------------------------------------
-        struct Entry { Point cm; int set; Fr extra; bool has_extra; };
+        struct Entry { Point cm; int set; };
         std::vector<Entry> table;
         for (uint32_t c = 0; c < h.n_advice; c++)
-            table.push_back({advice_cm[c], c < n_gate ? SET_0123 : c < n_gate + h.n_rlc ? SET_012 : SET_0, host::FR_ONE, false});
+            table.push_back({advice_cm[c], c < n_gate ? SET_0123 : c < n_gate + h.n_rlc ? SET_012 : SET_0});
         std::vector<uint32_t> fixed_idx;
         for (uint32_t f = 0; f < h.n_fixed; f++)
             if (!(f >= fx_l0 && f < fx_sigma)) fixed_idx.push_back(f);
-        for (uint32_t f : fixed_idx) table.push_back({fixed_cm[f], SET_0, host::FR_ONE, false});
+        for (uint32_t f : fixed_idx) table.push_back({fixed_cm[f], SET_0});
         for (uint32_t l = 0; l < h.n_lookup; l++) {
-            table.push_back({lookup_cm[2 * l], SET_0m1, host::FR_ONE, false});
-            table.push_back({lookup_cm[2 * l + 1], SET_0, host::FR_ONE, false});
-            table.push_back({zl_cm[l], SET_01, host::FR_ONE, false});
+            table.push_back({lookup_cm[2 * l], SET_0m1});
+            table.push_back({lookup_cm[2 * l + 1], SET_0});
+            table.push_back({zl_cm[l], SET_01});
         }
-        for (uint32_t j = 0; j < h.n_chunks; j++) table.push_back({zp_cm[j], j + 1 < h.n_chunks ? SET_01L : SET_01, host::FR_ONE, false});
-        table.push_back({r_cm, SET_0, host::FR_ONE, false});
+        for (uint32_t j = 0; j < h.n_chunks; j++) table.push_back({zp_cm[j], j + 1 < h.n_chunks ? SET_01L : SET_01});
+        table.push_back({r_cm, SET_0});
         const size_t n_written = table.size();                        // h_comb(x) is recomputed, not read
         std::vector<std::vector<Fr>> evals(n_written + 1);
         for (size_t i = 0; i < n_written; i++)
