@@ -220,6 +220,40 @@ def test_msm_small_value_hint_gives_identical_points(ctx):
         assert np.array_equal(got, want), f"small_values={small}"
 
 
+def test_msm_k16_long_skewed_columns_match_oracle(ctx):
+    """2^16-scalar columns (config 3/4 size): the cluster counting sort and the multi-level combine of hot buckets
+    (0/1-valued and constant columns put tens of thousands of references into one bucket), with and without the
+    small-value hint, against the C oracle."""
+    import torch
+    k, n = 16, 1 << 16
+    _, gl = toy_srs(k)
+    ctx.load_srs(k, g=None, g_lagrange=gl)
+    rng = np.random.default_rng(16)
+    pyr = random.Random(16)
+    cols = [random_fr_mont(rng, n),
+            fr_to_mont_array([pyr.randrange(2) for _ in range(n)]),                       # bits: one hot bucket
+            fr_to_mont_array([3] * n),                                                    # a constant column
+            fr_to_mont_array([pyr.randrange(1 << 61) if i % 9 else field.R_MOD - 1 - (i % 5) for i in range(n)])]
+    scal = np.ascontiguousarray(np.concatenate(cols))
+    want = cbind.msm(scal, gl, n, len(cols))
+    d = torch.from_numpy(scal.view(np.int64).reshape(-1)).cuda()
+    out = torch.zeros(len(cols) * 8, dtype=torch.int64, device="cuda")
+    for small in (False, True):
+        out.zero_()
+        ctx.msm_g1_dev(d.data_ptr(), len(cols), 1, out.data_ptr(), small_values=small)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(len(cols), 8), want), f"small_values={small}"
+    # the same columns ten times over (40 columns): the thread-fold path of the big commits
+    reps = 10
+    d2 = d.repeat(reps)
+    out2 = torch.zeros(reps * len(cols) * 8, dtype=torch.int64, device="cuda")
+    ctx.msm_g1_dev(d2.data_ptr(), reps * len(cols), 1, out2.data_ptr())
+    ctx.sync()
+    got2 = out2.cpu().numpy().view(np.uint64).reshape(reps, len(cols), 8)
+    for r in range(reps):
+        assert np.array_equal(got2[r], want)
+
+
 def test_srs_setup_on_gpu_matches_oracle(ctx):
     """zkfhe_srs_setup (ParamsKZG::setup shape) vs the oracle's g[i] = tau^i G, g_lagrange[i] = l_i(tau) G."""
     import zk_fhe_b200
