@@ -285,6 +285,11 @@ void zkfhe_proof_free(uint8_t* proof);
  * Fq2 = Fq[u]/(u^2+1)); every coordinate Montgomery (R = 2^256), identity = all zeros.  Host
  * arithmetic: one check per proof. */
 int zkfhe_pairing_check(const uint8_t* g1_points, const uint8_t* g2_points, uint32_t count, int* is_one);
+/* e(P, Q) itself: 12 Fq coefficients (Montgomery, 384 bytes) of an element of Fq[w]/(w^12 - 18 w^6 + 82), low degree
+ * first.  `reference_construction` != 0 computes it the plain way (Fq12 curve arithmetic, one 2790-bit
+ * exponentiation -- what oracle/pairing.py restates); 0 is the production path (Q on the twist over Fq2, sparse
+ * lines, Frobenius maps, the BN final-exponentiation chain).  Both return the same bytes. */
+int zkfhe_pairing(const uint8_t* g1_point, const uint8_t* g2_point, int reference_construction, uint8_t* out384);
 /* [tau]_2 of the test SRS made by zkfhe_srs_setup (halo2 `ParamsKZG::setup` keeps s_g2 beside the G1
  * powers): tau as a Montgomery Fr element in, 128 bytes (x.c0 | x.c1 | y.c0 | y.c1, Montgomery) out. */
 int zkfhe_srs_g2(const uint8_t* tau_mont32, uint8_t* out128);

@@ -71,3 +71,24 @@ def test_srs_g2_matches_oracle():
         t = fr_mont_bytes(tau)
         assert lib.zkfhe_srs_g2(_addr(t), _addr(out)) == 0
         assert bytes(out) == _g2(pairing.g2_mul(pairing.G2_GEN, tau))
+
+
+def test_pairing_values_fast_path_equals_reference_construction_equals_oracle():
+    """zkfhe_pairing: the production path (Q on the twist over Fq2, sparse lines, Frobenius maps, BN final-exponentiation
+    chain) returns bit for bit what the plain construction returns, and both equal the Python oracle's GT element."""
+    lib = zk_fhe_b200.load_library()
+    r_inv = pow(1 << 256, -1, P_MOD)
+    for a, b in ((1, 1), (0xABCDEF123456789, 0x1234567), (R_MOD - 2, 3)):
+        p1, q2 = curve.g1_mul(curve.G1_GEN, a), pairing.g2_mul(pairing.G2_GEN, b)
+        want = pairing.pairing(q2, p1).c
+        pb, qb = bytearray(_g1(p1)), bytearray(_g2(q2))
+        for reference_construction in (0, 1):
+            out = bytearray(384)
+            assert lib.zkfhe_pairing(_addr(pb), _addr(qb), reference_construction, _addr(out)) == 0
+            got = [int.from_bytes(out[32 * i:32 * i + 32], "little") * r_inv % P_MOD for i in range(12)]
+            assert got == want, (a, b, reference_construction)
+    one = bytearray(384)
+    zero_pt = bytearray(64)
+    qb = bytearray(_g2(pairing.G2_GEN))
+    assert lib.zkfhe_pairing(_addr(zero_pt), _addr(qb), 0, _addr(one)) == 0          # e(identity, Q) = 1
+    assert int.from_bytes(one[:32], "little") * r_inv % P_MOD == 1 and not any(one[32:])

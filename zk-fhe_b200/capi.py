@@ -48,6 +48,7 @@ _SIGNATURES = {
     "zkfhe_launch_count": (_c.c_uint64, [_c.c_void_p]),
     "zkfhe_selftest": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_uint32)]),
     "zkfhe_pairing_check": (_c.c_int, [_u8p, _u8p, _c.c_uint32, _c.POINTER(_c.c_int)]),
+    "zkfhe_pairing": (_c.c_int, [_u8p, _u8p, _c.c_int, _u8p]),
     "zkfhe_srs_g2": (_c.c_int, [_u8p, _u8p]),
     "zkfhe_vk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include "inv_bin.cuh"
 
 namespace zkfhe { namespace host {
 
@@ -76,7 +77,15 @@ inline Fq fq_mul(const Fq& a, const Fq& b) {
 inline Fq fq_to_mont(const Fq& canon) { return fq_mul(canon, FQ_R2); }
 inline Fq fq_from_mont(const Fq& m) { Fq one = {{1, 0, 0, 0}}; return fq_mul(m, one); }
 inline Fq fq_from_u64(uint64_t v) { Fq c = {{v, 0, 0, 0}}; return fq_to_mont(c); }
-inline Fq fq_inv(const Fq& a) {   // Fermat; inv(0) = 0
+static const Fq FQ_R3 = {{0xb1cd6dafda1530dfULL, 0x62f210e6a7283db6ULL, 0xef7f0b0c0ada0afbULL, 0x20fd6e902d592544ULL}};
+// inverse of a Montgomery-form element: binary extended Euclid on the raw limbs (inv_bin.cuh, the routine the
+// kernels use) gives (aR)^-1; one product with R^3 brings it back to a^-1 R.  inv(0) = 0.
+inline Fq fq_inv(const Fq& a) {
+    Fq t;
+    u256_inv_odd(reinterpret_cast<uint32_t*>(t.l), reinterpret_cast<const uint32_t*>(a.l), reinterpret_cast<const uint32_t*>(FQ_MOD.l));
+    return fq_mul(t, FQ_R3);
+}
+inline Fq fq_inv_fermat(const Fq& a) {   // the independent formulation, kept for the self check
     Fq e = FQ_MOD;
     e.l[0] -= 2;
     Fq acc = FQ_ONE;
@@ -290,16 +299,146 @@ inline Fq12 miller_loop(const G2Aff& q2, const G1Aff& p1) {
     return f;
 }
 
-inline Fq12 final_exponentiate(const Fq12& f) { return fq12_pow(f, FINAL_EXP_WORDS, FINAL_EXP_NWORDS); }
+inline Fq12 final_exponentiate_reference(const Fq12& f) { return fq12_pow(f, FINAL_EXP_WORDS, FINAL_EXP_NWORDS); }
+
+// ---- the production path: same pairing, ~40x fewer field operations ------------------------------------------
+// miller_loop / final_exponentiate_reference above are the plain construction oracle/pairing.py restates (Fq12 curve
+// arithmetic with Fq12 inversions, one 2790-bit exponentiation).  Below: the point Q stays on the twist over Fq2
+// (affine, one Fq inversion per step), a line is the sparse element  -yP + (lambda xP) w + (yA - lambda xA) w^3,
+// the Frobenius maps are coefficient-wise products with powers of gamma_1 = xi^((p-1)/6), and the final exponentiation
+// is (p^6 - 1)(p^2 + 1) by Frobenius / conjugation followed by the Devegili et al. chain for (p^4 - p^2 + 1)/r
+// (three exponentiations by the 63-bit BN parameter u).  miller_loop_fast returns bit-for-bit what miller_loop
+// returns, and final_exponentiate what final_exponentiate_reference returns (tests/test_pairing_cpu.py).
+inline Fq2 fq2_conj(const Fq2& a) { return Fq2{a.c0, fq_neg(a.c1)}; }
+inline Fq2 fq2_pow(const Fq2& a, const uint64_t* e, int words) {
+    Fq2 acc{FQ_ONE, FQ_ZERO};
+    for (int i = words - 1; i >= 0; i--)
+        for (int b = 63; b >= 0; b--) {
+            acc = fq2_mul(acc, acc);
+            if ((e[i] >> b) & 1) acc = fq2_mul(acc, a);
+        }
+    return acc;
+}
+// a + b u placed at w^pos:  (a - 9b) w^pos + b w^(pos+6), pos + 6 < 12
+inline void fq12_add_fq2_at(Fq12& f, const Fq2& v, int pos) {
+    static const Fq nine = fq_from_u64(9);
+    f.c[pos] = fq_add(f.c[pos], fq_sub(v.c0, fq_mul(nine, v.c1)));
+    f.c[pos + 6] = fq_add(f.c[pos + 6], v.c1);
+}
+struct PairingConsts {
+    Fq2 g12, g13;            // gamma_1^2, gamma_1^3: Frobenius of a twisted G2 point
+    Fq12 frob[12];           // gamma_1^i w^i: f^p = sum_i c_i frob[i]
+    PairingConsts() {
+        const Fq2 xi{fq_from_u64(9), FQ_ONE};
+        const Fq2 g1 = fq2_pow(xi, FROB_EXP_WORDS, 4);
+        g12 = fq2_mul(g1, g1);
+        g13 = fq2_mul(g12, g1);
+        Fq2 gi{FQ_ONE, FQ_ZERO};
+        Fq12 wi = fq12_one(), w = fq12_zero();
+        w.c[1] = FQ_ONE;
+        for (int i = 0; i < 12; i++) {
+            Fq12 emb = fq12_zero();
+            fq12_add_fq2_at(emb, gi, 0);
+            frob[i] = fq12_mul(emb, wi);
+            gi = fq2_mul(gi, g1);
+            wi = fq12_mul(wi, w);
+        }
+    }
+};
+inline const PairingConsts& pairing_consts() { static const PairingConsts c; return c; }
+
+inline Fq12 fq12_frobenius_fast(const Fq12& f) {
+    const PairingConsts& pc = pairing_consts();
+    Fq12 r = fq12_zero();
+    for (int i = 0; i < 12; i++) {
+        if (f.c[i].is_zero()) continue;
+        for (int j = 0; j < 12; j++)
+            if (!pc.frob[i].c[j].is_zero()) r.c[j] = fq_add(r.c[j], fq_mul(f.c[i], pc.frob[i].c[j]));
+    }
+    return r;
+}
+inline Fq12 fq12_conj(const Fq12& f) {               // f^(p^6): w -> -w
+    Fq12 r = f;
+    for (int i = 1; i < 12; i += 2) r.c[i] = fq_neg(r.c[i]);
+    return r;
+}
+
+// one Miller step on the twist: A <- A + B (or 2A when B is A), returns the line through them evaluated at P
+inline Fq12 line_and_step(G2Aff& A, const G2Aff& B, const G1Aff& P) {
+    Fq12 line = fq12_zero();
+    Fq2 lambda;
+    if (!fq2_eq(A.x, B.x)) {
+        lambda = fq2_mul(fq2_sub(B.y, A.y), fq2_inv(fq2_sub(B.x, A.x)));
+    } else if (fq2_eq(A.y, B.y)) {
+        lambda = fq2_mul(fq2_mul(fq2_small(3), fq2_mul(A.x, A.x)), fq2_inv(fq2_add(A.y, A.y)));
+    } else {                                         // vertical line xP - xA w^2 (A + B = identity): not met in the loop
+        line.c[0] = P.x;
+        fq12_add_fq2_at(line, Fq2{fq_neg(A.x.c0), fq_neg(A.x.c1)}, 2);
+        A.inf = true;
+        return line;
+    }
+    line.c[0] = fq_neg(P.y);
+    fq12_add_fq2_at(line, Fq2{fq_mul(lambda.c0, P.x), fq_mul(lambda.c1, P.x)}, 1);
+    fq12_add_fq2_at(line, fq2_sub(A.y, fq2_mul(lambda, A.x)), 3);
+    const Fq2 nx = fq2_sub(fq2_sub(fq2_mul(lambda, lambda), A.x), B.x);
+    const Fq2 ny = fq2_sub(fq2_mul(lambda, fq2_sub(A.x, nx)), A.y);
+    A.x = nx;
+    A.y = ny;
+    return line;
+}
+
+inline Fq12 miller_loop_fast(const G2Aff& Q, const G1Aff& P) {
+    const PairingConsts& pc = pairing_consts();
+    G2Aff R = Q;
+    Fq12 f = fq12_one();
+    for (int i = LOG_ATE_LOOP_COUNT; i >= 0; i--) {
+        const Fq12 l = line_and_step(R, R, P);
+        f = fq12_mul(l, fq12_mul(f, f));             // the sparse operand first: fq12_mul skips its zero coefficients
+        if ((ATE_LOOP_COUNT_LO >> i) & 1) f = fq12_mul(line_and_step(R, Q, P), f);
+    }
+    const G2Aff Q1{fq2_mul(fq2_conj(Q.x), pc.g12), fq2_mul(fq2_conj(Q.y), pc.g13), false};
+    G2Aff nQ2{fq2_mul(fq2_conj(Q1.x), pc.g12), fq2_mul(fq2_conj(Q1.y), pc.g13), false};
+    nQ2.y = Fq2{fq_neg(nQ2.y.c0), fq_neg(nQ2.y.c1)};
+    f = fq12_mul(line_and_step(R, Q1, P), f);
+    f = fq12_mul(line_and_step(R, nQ2, P), f);
+    return f;
+}
+
+inline Fq12 final_exponentiate(const Fq12& in) {
+    // easy part: in^((p^6 - 1)(p^2 + 1))
+    Fq12 t1 = fq12_mul(fq12_conj(in), fq12_inv(in));
+    t1 = fq12_mul(fq12_frobenius_fast(fq12_frobenius_fast(t1)), t1);
+    // hard part (p^4 - p^2 + 1)/r = p^3 + (6u^2 + 1) p^2 + (-36u^3 - 18u^2 - 12u + 1) p + (-36u^3 - 30u^2 - 18u - 2)
+    const uint64_t u[1] = {BN_U};
+    const Fq12 fp = fq12_frobenius_fast(t1), fp2 = fq12_frobenius_fast(fp), fp3 = fq12_frobenius_fast(fp2);
+    const Fq12 fu = fq12_pow(t1, u, 1), fu2 = fq12_pow(fu, u, 1), fu3 = fq12_pow(fu2, u, 1);
+    const Fq12 fu2p = fq12_frobenius_fast(fu2), fu3p = fq12_frobenius_fast(fu3);
+    const Fq12 y0 = fq12_mul(fq12_mul(fp, fp2), fp3);
+    const Fq12 y1 = fq12_conj(t1);
+    const Fq12 y2 = fq12_frobenius_fast(fu2p);
+    const Fq12 y3 = fq12_conj(fq12_frobenius_fast(fu));
+    const Fq12 y4 = fq12_conj(fq12_mul(fu, fu2p));
+    const Fq12 y5 = fq12_conj(fu2);
+    const Fq12 y6 = fq12_conj(fq12_mul(fu3, fu3p));
+    Fq12 t0 = fq12_mul(fq12_mul(fq12_mul(y6, y6), y4), y5);
+    Fq12 s1 = fq12_mul(fq12_mul(y3, y5), t0);
+    t0 = fq12_mul(t0, y2);
+    s1 = fq12_mul(fq12_mul(s1, s1), t0);
+    s1 = fq12_mul(s1, s1);
+    t0 = fq12_mul(s1, y1);
+    s1 = fq12_mul(s1, y0);
+    t0 = fq12_mul(t0, t0);
+    return fq12_mul(t0, s1);
+}
 
 // prod_i e(P_i, Q_i) == 1  (identity points contribute 1)
-inline bool pairing_product_is_one(const G1Aff* p, const G2Aff* q, int count) {
+inline bool pairing_product_is_one(const G1Aff* p, const G2Aff* q, int count, bool reference_construction = false) {
     Fq12 f = fq12_one();
     for (int i = 0; i < count; i++) {
         if (p[i].inf || q[i].inf) continue;
-        f = fq12_mul(f, miller_loop(q[i], p[i]));
+        f = fq12_mul(f, reference_construction ? miller_loop(q[i], p[i]) : miller_loop_fast(q[i], p[i]));
     }
-    return final_exponentiate(f) == fq12_one();
+    return (reference_construction ? final_exponentiate_reference(f) : final_exponentiate(f)) == fq12_one();
 }
 
 } }  // namespace zkfhe::host

@@ -89,6 +89,31 @@ int zkfhe_pairing_check(const uint8_t* g1_points, const uint8_t* g2_points, uint
     return ZKFHE_OK;
 }
 
+// e(P, Q) as an element of GT: 12 Fq coefficients (Montgomery) of Fq[w]/(w^12 - 18 w^6 + 82), low degree first.
+// reference_construction != 0 selects the plain construction (Fq12 curve arithmetic, one long exponentiation) that
+// oracle/pairing.py restates; both give the same 384 bytes.
+int zkfhe_pairing(const uint8_t* g1_point, const uint8_t* g2_point, int reference_construction, uint8_t* out384) {
+    if (!g1_point || !g2_point || !out384) return ZKFHE_ERR_ARG;
+    host::G1Aff p;
+    host::G2Aff q;
+    memcpy(&p.x, g1_point, 32);
+    memcpy(&p.y, g1_point + 32, 32);
+    p.inf = p.x.is_zero() && p.y.is_zero();
+    memcpy(&q.x.c0, g2_point, 32);
+    memcpy(&q.x.c1, g2_point + 32, 32);
+    memcpy(&q.y.c0, g2_point + 64, 32);
+    memcpy(&q.y.c1, g2_point + 96, 32);
+    q.inf = q.x.c0.is_zero() && q.x.c1.is_zero() && q.y.c0.is_zero() && q.y.c1.is_zero();
+    for (const host::Fq* c : {&p.x, &p.y, &q.x.c0, &q.x.c1, &q.y.c0, &q.y.c1})
+        if (host::fq_geq(*c, host::FQ_MOD)) return ZKFHE_ERR_ARG;
+    host::Fq12 e = host::fq12_one();
+    if (!p.inf && !q.inf)
+        e = reference_construction ? host::final_exponentiate_reference(host::miller_loop(q, p))
+                                   : host::final_exponentiate(host::miller_loop_fast(q, p));
+    memcpy(out384, e.c, 384);
+    return ZKFHE_OK;
+}
+
 // [tau]_2 for the test SRS (`ParamsKZG::setup` keeps s_g2 next to the G1 powers): 128 bytes, Montgomery.
 int zkfhe_srs_g2(const uint8_t* tau_mont32, uint8_t* out128) {
     if (!tau_mont32 || !out128) return ZKFHE_ERR_ARG;
