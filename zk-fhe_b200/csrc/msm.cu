@@ -671,6 +671,8 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     // 3*groups/32 point additions).
     uint32_t log_fold = 4;
     while (log_fold && (NB >> log_fold) == 0) log_fold--;
+    // narrow-window commits have 8x fewer buckets: shorter fold chains keep a full GPU's worth of threads
+    while (log_fold > 2 && (uint64_t)batch * (NB >> log_fold) < 32768) log_fold--;
     while ((NB >> log_fold) > 512u) log_fold++;
     const bool warp_fold = batch < 32 && NB >= 1024 && (NB >> 5) <= 512u;     // few columns: the latency variant
     if (warp_fold) log_fold = 5;
