@@ -243,6 +243,23 @@ static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch
     const size_t smem = (size_t)T * sizeof(fr_t);
     // process-wide attribute: always the fixed maximum (4096-element tile), never this call's size
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(fr_t)));
+    {   // field products this pass issues (zkfhe_timing_get category 6), in eighths per element: one per butterfly,
+        // minus the butterflies of round 0 whose twiddle is 1 or whose operand is structurally zero, plus the
+        // per-element 4-step twiddle / coset / n^-1 factors
+        const uint64_t elems = (uint64_t)batch << p.log_n;
+        const uint32_t r0 = p.rounds[0];
+        uint32_t skipped8 = r0 == 3 ? 7 : r0 == 2 ? 6 : r0 == 1 ? 4 : 0;
+        if (r0 == 3 && p.zero_stages == 2) skipped8 = 9;
+        else if (r0 == 3 && p.zero_stages == 3) skipped8 = 12;
+        else if (r0 == 2 && p.zero_stages == 2) skipped8 = 8;
+        uint64_t eighths = 4ull * p.log_r - skipped8;
+        if (p.mode == 0) eighths += 8;
+        if (p.post_scale) eighths += 8;
+        if (p.post_coset) eighths += 16 / 3;
+        uint64_t prod = elems * eighths / 8;
+        if (p.pre_coset) prod += (uint64_t)batch * (p.in_len < (1u << p.log_n) ? p.in_len : (1u << p.log_n)) * 2 / 3;
+        ctx->ntt_products += prod;
+    }
     dim3 grid(tiles, batch);
     k_ntt_pass<<<grid, threads, smem, ctx->stream>>>(p);
     ZK_CHECK_LAUNCH(ctx);
@@ -293,13 +310,6 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         ZK_TRY(launch_pass(ctx, p, 1u << (log_ra - p.log_l), batch));
     }
     ZK_TRY(timed_end(ctx));
-    {   // products issued: one per butterfly, plus the per-element 4-step twiddle, coset and n^-1 factors (x3 = thirds)
-        const uint64_t elems = (uint64_t)batch << log_n;
-        uint64_t thirds = (log_n > 11 ? 3 : 0) + (coset ? 2 : 0) + (inverse && log_n <= 11 ? 3 : 0);
-        uint32_t z = 0;                  // copy-only stages of a zero-extended pass A issue no products
-        while (log_n > 11 && z < 3 && ((uint64_t)in_len << (z + 1)) <= ((uint64_t)1 << log_n)) z++;
-        ctx->ntt_products += elems / 2 * (log_n - z) + elems * thirds / 3;
-    }
     return ZKFHE_OK;
 }
 
