@@ -15,11 +15,12 @@
 // adjacent columns (L*32-byte contiguous runs), in pass B L whole rows.  n <= 2048
 // is a single pass-B launch with L = 1.
 //
-// Inside a pass the log2(R) radix-2 DIT stages are grouped into ROUNDS of three
-// (radix-8 in registers: 8 elements, 12 butterflies, 7 twiddles per thread).  The
-// first round reads its operands straight from HBM (bit-reversed gather) and the
-// last one writes straight back, so a 6-stage pass exchanges data through shared
-// memory once and a 7/8-stage pass twice, instead of once per stage; an element
+// Inside a pass the log2(R) radix-2 DIT stages are grouped into ROUNDS done in
+// registers (NTT_MAX_LR stages each: radix-4 = 4 elements, 4 butterflies, 3
+// twiddles per thread and group; radix-8 is compiled by setting NTT_MAX_LR = 3).
+// The first round reads its operands straight from HBM (bit-reversed gather) and
+// the last one writes straight back, so a 6-stage pass exchanges data through
+// shared memory twice and a 7/8-stage pass three times, instead of once per stage; an element
 // moves HBM->SM->HBM once per pass: 2 x 64 B per element per transform against
 // 64 B algorithmic.  Shared memory holds the tile as two 16-byte planes (low and
 // high halves of every element) so that a quarter-warp's 128-bit accesses cover
@@ -65,6 +66,12 @@ struct NttPass {
     uint8_t rounds[8];                // stages per round (3, 2, 1; a trailing 0 = plain copy-out)
     fr_t n_inv, zeta, zeta2;
 };
+
+// stages per register round.  Measured on B200: 3 = radix-8 (114 registers, 4 CTAs of 128 threads per SM, one shared-
+// memory exchange per 6-stage pass) against 2 = radix-4 (80 registers, 6 CTAs per SM, one more exchange per pass):
+// radix-4 is 6-9 % faster at 2^13 .. 2^18 -- the pass is bound by dependent-IMAD latency, so warps in flight matter
+// more than shared-memory round trips.
+static constexpr int NTT_MAX_LR = 2;
 
 extern __shared__ uint4 ntt_smem[];
 
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
     for (uint32_t ri = 0; ri < p.n_rounds; ri++) {
         const uint32_t r = p.rounds[ri];
         const bool first = ri == 0, last = ri + 1 == p.n_rounds;
-        if (r == 3) ntt_round<3>(p, Slo, Shi, s, first, last, in, out);
+        if (NTT_MAX_LR >= 3 && r == 3) ntt_round<NTT_MAX_LR>(p, Slo, Shi, s, first, last, in, out);
         else if (r == 2) ntt_round<2>(p, Slo, Shi, s, first, last, in, out);
         else if (r == 1) ntt_round<1>(p, Slo, Shi, s, first, last, in, out);
         else ntt_round<0>(p, Slo, Shi, s, first, last, in, out);
@@ -223,7 +230,8 @@ static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch
     const uint32_t T = 1u << (p.log_r + p.log_l);
     // rounds of three stages; a remainder of one is taken as 2 + 2 so no round is a lone radix-2
     uint32_t left = p.log_r, nr = 0;
-    while (left > 4 || left == 3) { p.rounds[nr++] = 3; left -= 3; }
+    while (NTT_MAX_LR >= 3 && (left > 4 || left == 3)) { p.rounds[nr++] = 3; left -= 3; }
+    while (NTT_MAX_LR < 3 && left > 2) { p.rounds[nr++] = 2; left -= 2; }
     if (left == 4) { p.rounds[nr++] = 2; p.rounds[nr++] = 2; }
     else if (left) p.rounds[nr++] = (uint8_t)left;
     if (nr < 2) p.rounds[nr++] = 0;      // never load and store in the same round: an in-place pass would race
@@ -239,7 +247,9 @@ static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch
             z++;
         p.zero_stages = z;
     }
-    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 128 ? 128 : T / 8);     // 136 registers: 3 CTAs of 128 per SM
+    // 128 threads per 1024-element tile (two radix-4 groups per thread and round): 80 registers, 6 CTAs per SM;
+    // 256-thread CTAs (one group per thread) measured 2-5 % slower
+    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 128 ? 128 : T / 8);
     const size_t smem = (size_t)T * sizeof(fr_t);
     // process-wide attribute: always the fixed maximum (4096-element tile), never this call's size
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(fr_t)));
