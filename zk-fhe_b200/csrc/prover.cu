@@ -39,44 +39,6 @@ enum { SET_0 = 0, SET_0123 = 1, SET_012 = 2, SET_0m1 = 3, SET_01 = 4, SET_01L = 
 // distinct points, index into pw tables: x*w^{-1}, x, x*w, x*w^2, x*w^3, x*w^last
 static int point_index(int rot) { return rot == ROT_LAST ? 5 : rot + 1; }
 
-// ---- ChaCha20 (RFC 7539) stream for blinding factors --------------------------------------------
-struct ChaCha20 {
-    uint32_t st[16];
-    uint8_t block[64];
-    int used = 64;
-    static uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
-    explicit ChaCha20(const uint8_t key[32]) {
-        static const uint32_t c[4] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
-        memcpy(st, c, 16);
-        memcpy(st + 4, key, 32);
-        st[12] = 0; st[13] = 0; st[14] = 0; st[15] = 0;
-    }
-    void next_block() {
-        uint32_t x[16];
-        memcpy(x, st, 64);
-#define ZK_QR(a, b, c, d) x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12); \
-                          x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
-        for (int i = 0; i < 10; i++) {
-            ZK_QR(0, 4, 8, 12) ZK_QR(1, 5, 9, 13) ZK_QR(2, 6, 10, 14) ZK_QR(3, 7, 11, 15)
-            ZK_QR(0, 5, 10, 15) ZK_QR(1, 6, 11, 12) ZK_QR(2, 7, 8, 13) ZK_QR(3, 4, 9, 14)
-        }
-#undef ZK_QR
-        for (int i = 0; i < 16; i++) x[i] += st[i];
-        memcpy(block, x, 64);
-        if (++st[12] == 0) ++st[13];
-        used = 0;
-    }
-    void fill(void* out, size_t len) {
-        uint8_t* p = (uint8_t*)out;
-        while (len) {
-            if (used == 64) next_block();
-            size_t take = (size_t)(64 - used) < len ? (size_t)(64 - used) : len;
-            memcpy(p, block + used, take);
-            used += (int)take; p += take; len -= take;
-        }
-    }
-};
-
 // ---- kernels --------------------------------------------------------------------------------------
 struct ColSrc {            // one advice column cut from a flat context
     const fr_t* base;      // flat cells of the context (or lookup cells)
@@ -100,11 +62,34 @@ __global__ void k_fill_instance(fr_t* inst, uint32_t n, const fr_t* const* bases
     if (row < count) v = fe_load(bases[cell_ctx(ids[row])] + cell_off(ids[row]));
     fe_store(inst + row, v);
 }
-// 255-bit random integers -> uniform-ish Fr (Montgomery)
-__global__ void k_random_to_fr(fr_t* d, uint32_t count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Blinding factors straight from the ChaCha20 keystream, on the device: element i of a request that starts at
+// 32-byte stream position `pos32` is half ((pos32 + i) & 1) of keystream block (pos32 + i) >> 1 (counter in words
+// 12/13, zero nonce, key = the caller's 32-byte seed; byte-identical to generating the stream on the host and copying
+// it over, which is what this replaced), top bit cleared, then into Montgomery form: a 255-bit integer -> uniform-ish Fr.
+struct ChaChaKey { uint32_t k[8]; };
+__global__ void k_chacha_fr(fr_t* d, uint32_t count, ChaChaKey key, uint64_t pos32) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    fr_t v = fe_load(d + i);
+    const uint64_t e = pos32 + i, ctr = e >> 1;
+    uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3],
+                       key.k[4], key.k[5], key.k[6], key.k[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = st[j];
+#define ZK_DQR(a, b, c, d) x[a] += x[b]; x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 16); x[c] += x[d]; \
+                           x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 12); x[a] += x[b];               \
+                           x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 8); x[c] += x[d];                \
+                           x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 7);
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        ZK_DQR(0, 4, 8, 12) ZK_DQR(1, 5, 9, 13) ZK_DQR(2, 6, 10, 14) ZK_DQR(3, 7, 11, 15)
+        ZK_DQR(0, 5, 10, 15) ZK_DQR(1, 6, 11, 12) ZK_DQR(2, 7, 8, 13) ZK_DQR(3, 4, 9, 14)
+    }
+#undef ZK_DQR
+    const uint32_t half = (uint32_t)(e & 1) * 8;
+    fr_t v;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v.v[j] = half ? x[8 + j] + st[8 + j] : x[j] + st[j];
     v.v[7] &= 0x7fffffffu;
     fe_store(d + i, to_mont(v));
 }
@@ -481,7 +466,8 @@ struct zkfhe_prover {
     zkfhe_pk* pk = nullptr;
     zkfhe_ctx* ctx = nullptr;
     host::Transcript tr;
-    ChaCha20 rng;
+    zkfhe::ChaChaKey rng_key;           // blinding stream: ChaCha20 keyed by the caller's seed, generated on the device
+    uint64_t rng_pos32 = 0;      // stream position in 32-byte units
     int stage = 0;
     uint32_t C_all = 0, ap_base = 0, zp_base = 0, zl_base = 0, r_col = 0, lookup_adv_base = 0;
     fr_t *P = nullptr, *E = nullptr, *inst = nullptr, *inst_ext = nullptr, *blind = nullptr, *misc = nullptr;
@@ -497,7 +483,7 @@ struct zkfhe_prover {
         round_ms[i] = std::chrono::duration<double, std::milli>(now - t_mark).count();
         t_mark = now;
     }
-    zkfhe_prover(const uint8_t seed[32], int kind) : tr(kind), rng(seed) {}
+    zkfhe_prover(const uint8_t seed[32], int kind) : tr(kind) { memcpy(rng_key.k, seed, 32); }
 };
 
 namespace zkfhe {
@@ -522,12 +508,10 @@ static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count
 // fresh blinding factors: `count` Fr elements (Montgomery) at pr->blind + offset
 static int fill_random(zkfhe_prover* pr, size_t offset, uint32_t count) {
     zkfhe_ctx* ctx = pr->ctx;
-    std::vector<uint8_t> h((size_t)count * 32);
-    pr->rng.fill(h.data(), h.size());
-    ZK_CUDA(ctx, cudaMemcpyAsync(pr->blind + offset, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
-    k_random_to_fr<<<(count + 255) / 256, 256, 0, ctx->stream>>>(pr->blind + offset, count);
+    if (!count) return ZKFHE_OK;
+    k_chacha_fr<<<(count + 255) / 256, 256, 0, ctx->stream>>>(pr->blind + offset, count, pr->rng_key, pr->rng_pos32);
     ZK_CHECK_LAUNCH(ctx);
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // `h` is about to go out of scope
+    pr->rng_pos32 += count;              // no host round trip: the keystream is generated where it is consumed
     return ZKFHE_OK;
 }
 
@@ -566,7 +550,8 @@ int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32) {
     if (!pr || !seed32) return ZKFHE_ERR_ARG;
     const int kind = pr->tr.kind;
     pr->tr = host::Transcript(kind);
-    pr->rng = ChaCha20(seed32);
+    memcpy(pr->rng_key.k, seed32, 32);
+    pr->rng_pos32 = 0;
     pr->stage = 0;
     return ZKFHE_OK;
 }
