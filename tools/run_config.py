@@ -18,6 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 TAU = 0x5EED5EED5EED5EED5EED5EED
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+R_INV = pow(1 << 256, -1, R_MOD)
 
 
 def main():
@@ -64,8 +66,8 @@ def main():
         proof = pr.finish(circ.wit)
         ctx.sync()
         t1 = time.perf_counter()
-        from tests.util import mont_array_to_fr
-        inst = mont_array_to_fr(circ.wit.download(4))
+        raw = circ.wit.download(4)                     # (instances, 4) uint64, Montgomery
+        inst = [int.from_bytes(row.tobytes(), "little") * R_INV % R_MOD for row in raw]
         t2 = time.perf_counter()
         ok = prover.verify(ctx, vkb, inst, proof, s_g2)
         t3 = time.perf_counter()
