@@ -252,14 +252,22 @@ int zkfhe_pk_download_fixed(const zkfhe_pk* pk, uint32_t index, uint32_t form, u
 /* The verifying key's commitments: n_fixed G1Affine (Montgomery, 64 bytes each). */
 int zkfhe_pk_fixed_commitments(const zkfhe_pk* pk, uint8_t* h_out);
 
+/* data/<name>.pk (README.md:38: `keygen` writes it once, `prove` reads it many times): the layout of the circuit,
+ * the public cells, the fixed columns in Lagrange form and their commitments.  Coefficient / extended forms are
+ * recomputed on import (two batched NTTs).  Call export with buf = NULL to get the size.  The SRS for the key's k must
+ * be loaded on `ctx` before import. */
+int zkfhe_pk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed);
+int zkfhe_pk_import(zkfhe_ctx* ctx, const uint8_t* buf, size_t len, zkfhe_pk** out);
+
 /* ---- prove -------------------------------------------------------------------------------
  * `cargo run --example bfv -- ... prove` (README.md:40-46): snark-verifier-sdk `gen_snark_shplonk`
  * -> halo2 `create_proof`.  The Challenge API makes it two-phase (examples/bfv.rs:92-98): the
  * phase-0 witness is committed first, the challenge gamma comes back, the caller then runs the
  * phase-1 chip calls (the reference's callback) and finishes the proof.
- *   seed32            ChaCha20 key for the blinding factors (the reference uses OS entropy)
- *   transcript_kind   0 = BLAKE2b (halo2's native transcript; default), 1 = Poseidon (the hash
- *                     family of the reference's snark-verifier transcript; ~tens of ms on the host)
+ *   seed32            ChaCha20 key for the blinding factors (the reference uses OS entropy: callers should too)
+ *   transcript_kind   1 = Poseidon (what the reference's `prove` runs: snark-verifier's PoseidonTranscript, t = 5,
+ *                     rate 4, R_F = 8, R_P = 60; ~1,700 permutations per config-1 proof on the host),
+ *                     0 = BLAKE2b (halo2's native transcript; microseconds)
  * The proof is a malloc'd byte string (free with zkfhe_proof_free): commitments as canonical
  * uncompressed points (64 bytes), scalars canonical little-endian (32 bytes), in round order. */
 typedef struct zkfhe_prover zkfhe_prover;
@@ -303,6 +311,16 @@ int zkfhe_vk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed
  * reason for a rejection is zkfhe_last_error); error codes are for malformed arguments only. */
 int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t* instances, uint32_t n_instances,
                  const uint8_t* proof, size_t proof_len, const uint8_t* s_g2, int transcript_kind, int* accepted);
+
+/* ---- transcript (host arithmetic; callable without a GPU) ----------------------------------
+ * The Poseidon permutation behind transcript kind 1 on five Fr elements (Montgomery, 160 bytes, in place):
+ * plain = 0 is the optimised form the transcript runs (sparse partial rounds), plain != 0 the textbook form over
+ * (round constants, MDS); both return the same state.  Non-canonical input is ZKFHE_ERR_ARG. */
+int zkfhe_poseidon_permute(uint8_t* state160, int plain);
+/* Replay a message script through a fresh transcript of the given kind: op 1 + 32 bytes = common_scalar (canonical
+ * little-endian), op 2 + 64 bytes = common_point (canonical x | y), op 3 = squeeze; the challenges are written to
+ * `out` as canonical 32-byte scalars (out = NULL only counts them). */
+int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges);
 
 /* ---- timing hook -------------------------------------------------------------------------
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last

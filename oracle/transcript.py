@@ -4,9 +4,13 @@ zk-fhe_b200/csrc/host_ff.h so that the verifier replays exactly what the prover 
   Blake2bTranscript   halo2 `Blake2bWrite`/`Challenge255` shape [UPSTREAM-RECALL]: running
                       BLAKE2b-512 with one-byte tags; a challenge is the digest of the state so
                       far reduced from 512 bits (halo2curves `from_uniform_bytes`).
-  PoseidonTranscript  the hash family of snark-verifier's PoseidonTranscript (t=5, rate 4, R_F=8,
-                      R_P=60) with constants from the published Grain-LFSR procedure.  The upstream
-                      crates are un-vendored: equality with their tables is UNPINNED.
+  PoseidonTranscript  snark-verifier's PoseidonTranscript<NativeLoader> over the PSE `poseidon` crate
+                      (t=5, rate 4, R_F=8, R_P=60) [UPSTREAM-RECALL]: state[0] starts at 2^64, scalars
+                      are absorbed natively, points as (x mod r, y mod r), a squeeze pads with one 1.
+                      Constants come from the published Grain-LFSR procedure; the procedure and the
+                      permutation below are PINNED by the published t=3 / t=2 vectors
+                      (tests/test_oracle_transcript.py); the t=5 tables themselves have no published
+                      vector offline (the upstream crates are un-vendored).
 """
 import hashlib
 
@@ -36,7 +40,7 @@ class Blake2bTranscript:
 T, R_F, R_P, N_BITS = 5, 8, 60, 254
 
 
-def _grain_bits():
+def _grain_bits(T=T, R_F=R_F, R_P=R_P):
     state = []
     for val, width in ((1, 2), (0, 4), (N_BITS, 12), (T, 12), (R_F, 10), (R_P, 10)):
         state += [(val >> (width - 1 - i)) & 1 for i in range(width)]
@@ -58,8 +62,9 @@ def _grain_bits():
         yield step()
 
 
-def poseidon_params():
-    g = _grain_bits()
+def poseidon_params(T=T, R_F=R_F, R_P=R_P):
+    """(round constants, MDS matrix) of Poseidon-x^5 over BN254 Fr for the given width / round numbers."""
+    g = _grain_bits(T, R_F, R_P)
 
     def bits(n):
         v = 0
@@ -85,11 +90,15 @@ def poseidon_params():
 _PARAMS = None
 
 
-def poseidon_permute(s):
+def poseidon_permute(s, params=None, R_F=R_F, R_P=R_P):
+    """The plain (textbook) permutation; `params` defaults to the transcript's t=5 tables."""
     global _PARAMS
-    if _PARAMS is None:
-        _PARAMS = poseidon_params()
-    rc, mds = _PARAMS
+    if params is None:
+        if _PARAMS is None:
+            _PARAMS = poseidon_params()
+        params = _PARAMS
+    rc, mds = params
+    T = len(mds)
     half = R_F // 2
     for r in range(R_F + R_P):
         s = [(s[i] + rc[r * T + i]) % R_MOD for i in range(T)]
@@ -103,7 +112,7 @@ def poseidon_permute(s):
 
 class PoseidonTranscript:
     def __init__(self):
-        self.state = [0x7A6B666865] + [0] * (T - 1)
+        self.state = [1 << 64] + [0] * (T - 1)
         self.buf = []
 
     def common_scalar(self, x):
@@ -111,8 +120,7 @@ class PoseidonTranscript:
 
     def common_point(self, pt):
         x, y = (0, 0) if pt is None else pt
-        for c in (x, y):
-            self.buf += [c & ((1 << 128) - 1), c >> 128]
+        self.buf += [x % R_MOD, y % R_MOD]
 
     def squeeze(self):
         self.buf.append(1)

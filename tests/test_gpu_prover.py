@@ -95,6 +95,51 @@ def _prove(ctx, pk, inp, seed, params=None, transcript=0):
     return proof, inst
 
 
+def _pverify(ctx, *args, **kw):
+    """The product verifier on the BLAKE2b transcript (the mutation sweeps below replay the proof dozens of times; the
+    oracle's pure-Python Poseidon costs ~2.5 s per replay, so they run on the cheap hash -- the Poseidon default has
+    its own test)."""
+    from zk_fhe_b200 import prover
+    kw.setdefault("transcript", 0)
+    return prover.verify(ctx, *args, **kw)
+
+
+def test_prove_with_the_default_poseidon_transcript(ctx13, pk13, bfv_input):
+    """The configuration the reference's `prove` runs (snark-verifier PoseidonTranscript) is the default of
+    Prover / prove / verify: both verifiers accept, both reject a flipped bit and the other hash."""
+    from zk_fhe_b200 import bfv, prover
+    proof, circ = prover.prove(pk13, lambda: bfv.BfvCircuit(ctx13), bfv_input, bytes(range(32)))
+    inst = mont_array_to_fr(circ.wit.download(4))
+    vk, vkb, s_g2 = _vk(pk13, 109), pk13.vk_bytes(), ctx13.srs_g2(TAU)
+    assert verifier.verify(vk, inst, proof, TAU, transcript_kind=1)
+    assert prover.verify(ctx13, vkb, inst, proof, s_g2)
+    assert not prover.verify(ctx13, vkb, inst, proof, s_g2, transcript=0)
+    bad = bytearray(proof)
+    bad[64 * 200 + 7] ^= 4
+    assert not prover.verify(ctx13, vkb, inst, bytes(bad), s_g2)
+    with pytest.raises(verifier.VerifyError):
+        verifier.verify(vk, inst, bytes(bad), TAU, transcript_kind=1)
+    # a second proof with OS-entropy blinding (the default seed) differs and verifies
+    proof2, _ = prover.prove(pk13, lambda: bfv.BfvCircuit(ctx13), bfv_input)
+    assert proof2 != proof and prover.verify(ctx13, vkb, inst, proof2, s_g2)
+
+
+def test_proving_key_file_round_trip(ctx13, pk13, bfv_input):
+    """data/<name>.pk (README.md:38): export, import on the same SRS, same proof bytes for the same seed."""
+    from zk_fhe_b200 import prover
+    blob = pk13.export_bytes()
+    assert len(blob) > pk13.info["n_fixed"] * 8192 * 32
+    pk2 = prover.import_key(ctx13, blob)
+    assert pk2.info == pk13.info and pk2.pinning() == pk13.pinning() and pk2.vk_bytes() == pk13.vk_bytes()
+    a, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    b, _ = _prove(ctx13, pk2, bfv_input, bytes(range(32)))
+    assert a == b
+    from zk_fhe_b200.capi import ZkfheError
+    for bad in (blob[:-1], b"XX" + blob[2:], blob[:64]):
+        with pytest.raises(ZkfheError):
+            prover.import_key(ctx13, bad)
+
+
 def test_prove_bfv_in_and_oracle_verifier_accepts(ctx13, pk13, bfv_input):
     proof, inst = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
     assert inst[:1024] == [int(x) for x in bfv_input["pk0"]]
@@ -134,7 +179,7 @@ def test_product_verifier_agrees_with_oracle_verifier(ctx13, pk13, bfv_input):
     vkb, s_g2 = pk13.vk_bytes(), ctx13.srs_g2(TAU)
     vk = _vk(pk13, 109)
     assert len(vkb) == 72 + 64 * pk13.info["n_fixed"]
-    assert prover.verify(ctx13, vkb, inst, proof, s_g2)
+    assert _pverify(ctx13, vkb, inst, proof, s_g2)
     assert verifier.verify(vk, inst, proof, TAU)
     # verifying borrows the commitment-key slot for its MSM and must give it back intact
     proof2, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
@@ -145,24 +190,32 @@ def test_product_verifier_agrees_with_oracle_verifier(ctx13, pk13, bfv_input):
     for off in offsets:
         bad = bytearray(proof)
         bad[off] ^= 1 << rng.randrange(8)
-        assert not prover.verify(ctx13, vkb, inst, bytes(bad), s_g2), off
+        assert not _pverify(ctx13, vkb, inst, bytes(bad), s_g2), off
         assert "rejected" in ctx13.last_rejection
         with pytest.raises(verifier.VerifyError):
             verifier.verify(vk, inst, bytes(bad), TAU)
-    assert not prover.verify(ctx13, vkb, inst, proof[:-1], s_g2)
-    assert not prover.verify(ctx13, vkb, inst, proof + b"\0", s_g2)
+    assert not _pverify(ctx13, vkb, inst, proof[:-1], s_g2)
+    assert not _pverify(ctx13, vkb, inst, proof + b"\0", s_g2)
     bad_inst = list(inst)
     bad_inst[2048 + 17] = (bad_inst[2048 + 17] + 1) % 536870909
-    assert not prover.verify(ctx13, vkb, bad_inst, proof, s_g2)
-    assert not prover.verify(ctx13, vkb, inst[:-1], proof, s_g2)
-    assert not prover.verify(ctx13, vkb, inst, proof, ctx13.srs_g2(TAU + 1))          # another SRS
+    assert not _pverify(ctx13, vkb, bad_inst, proof, s_g2)
+    assert not _pverify(ctx13, vkb, inst[:-1], proof, s_g2)
+    assert not _pverify(ctx13, vkb, inst, proof, ctx13.srs_g2(TAU + 1))          # another SRS
     bad_vk = bytearray(vkb)
     bad_vk[72 + 64 * 200 + 7] ^= 4                                                      # a fixed commitment
-    assert not prover.verify(ctx13, bytes(bad_vk), inst, proof, s_g2)
+    assert not _pverify(ctx13, bytes(bad_vk), inst, proof, s_g2)
     import zk_fhe_b200
     with pytest.raises(zk_fhe_b200.ZkfheError):
-        prover.verify(ctx13, vkb[:-3], inst, proof, s_g2)                               # malformed key: an error, not a verdict
-    assert prover.verify(ctx13, vkb, inst, proof, s_g2)
+        _pverify(ctx13, vkb[:-3], inst, proof, s_g2)                               # malformed key: an error, not a verdict
+    # `usable` (header word 9) and `n_chunks` (word 8) are not in the digest: a key that carries anything but the
+    # values the layout implies is refused outright
+    for word, delta in ((9, -1), (9, 1), (8, 1)):
+        hdr = bytearray(vkb)
+        off = 8 + 4 * word
+        hdr[off:off + 4] = (int.from_bytes(hdr[off:off + 4], "little") + delta).to_bytes(4, "little")
+        with pytest.raises(zk_fhe_b200.ZkfheError):
+            _pverify(ctx13, bytes(hdr), inst, proof, s_g2)
+    assert _pverify(ctx13, vkb, inst, proof, s_g2)
 
 
 def test_proof_of_a_wrong_ciphertext_is_rejected(ctx13, pk13, bfv_input):

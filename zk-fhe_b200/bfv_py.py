@@ -8,6 +8,10 @@ recomputes), and the result has the schema of examples/bfv.rs:50-61 (nine arrays
 highest-degree coefficient first).
 
     python -m zk_fhe_b200.bfv_py --n 1024 --q 536870909 --t 7 --b 19 --seed 0 --out data/bfv/synth.in
+
+TEST / BENCHMARK INPUT GENERATOR ONLY: secrets, encryption randomness and errors come from a SEEDED numpy
+generator (default seed 0), so every value in the file is publicly reproducible.  Do not use it to encrypt
+anything real; a real front-end samples s, u, e0, e1 from a CSPRNG.
 """
 import argparse
 import json

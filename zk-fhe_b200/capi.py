@@ -53,6 +53,10 @@ _SIGNATURES = {
     "zkfhe_vk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,
                                 _c.POINTER(_c.c_int)]),
+    "zkfhe_poseidon_permute": (_c.c_int, [_u8p, _c.c_int]),
+    "zkfhe_transcript_replay": (_c.c_int, [_c.c_int, _u8p, _c.c_size_t, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
+    "zkfhe_pk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
+    "zkfhe_pk_import": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_void_p)]),
     "zkfhe_microbench": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint64)]),
     "zkfhe_ntt_fr": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),
     "zkfhe_ntt_fr_dev": (_c.c_int, [_c.c_void_p, _u8p, _c.c_uint32, _c.c_uint32, _c.c_int, _c.c_int]),

@@ -4,6 +4,7 @@
 #include <new>
 #include <cstring>
 #include "common.cuh"
+#include "host_ff.h"
 
 using namespace zkfhe;
 
@@ -164,7 +165,53 @@ int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t
 // ---- lifecycle ---------------------------------------------------------------------------
 extern "C" {
 
-const char* zkfhe_version(void) { return "zkfhe_b200 0.1 (sm_100a)"; }
+const char* zkfhe_version(void) { return "zkfhe_b200 0.2 (sm_100a)"; }
+
+// ---- host-only hooks: the Fiat-Shamir transcript, testable without a GPU ----------------------------------------
+int zkfhe_poseidon_permute(uint8_t* state160, int plain) {
+    if (!state160) return ZKFHE_ERR_ARG;
+    host::Fr s[POSEIDON_T];
+    memcpy(s, state160, sizeof s);
+    for (auto& v : s)
+        if (host::geq(v, host::FR_MOD)) return ZKFHE_ERR_ARG;
+    if (plain) host::poseidon_permute_plain(s); else host::poseidon_permute(s);
+    memcpy(state160, s, sizeof s);
+    return ZKFHE_OK;
+}
+
+int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges) {
+    if (!script || !n_challenges || (kind != host::TRANSCRIPT_BLAKE2B && kind != host::TRANSCRIPT_POSEIDON)) return ZKFHE_ERR_ARG;
+    host::Transcript tr(kind);
+    size_t pos = 0, count = 0;
+    while (pos < len) {
+        const uint8_t op = script[pos++];
+        if (op == 1) {                                   // scalar
+            if (pos + 32 > len) return ZKFHE_ERR_ARG;
+            host::Fr c;
+            memcpy(c.l, script + pos, 32);
+            pos += 32;
+            if (host::geq(c, host::FR_MOD)) return ZKFHE_ERR_ARG;
+            tr.common_scalar(host::to_mont(c));
+        } else if (op == 2) {                            // point
+            if (pos + 64 > len) return ZKFHE_ERR_ARG;
+            uint64_t xy[8];
+            memcpy(xy, script + pos, 64);
+            pos += 64;
+            tr.common_point(xy, xy + 4);
+        } else if (op == 3) {                            // squeeze
+            const host::Fr c = host::from_mont(tr.squeeze());
+            if (out) {
+                if ((count + 1) * 32 > cap) return ZKFHE_ERR_ARG;
+                memcpy(out + count * 32, c.l, 32);
+            }
+            count++;
+        } else {
+            return ZKFHE_ERR_ARG;
+        }
+    }
+    *n_challenges = count;
+    return ZKFHE_OK;
+}
 
 int zkfhe_init(int device, zkfhe_ctx** out) {
     if (!out) return ZKFHE_ERR_ARG;

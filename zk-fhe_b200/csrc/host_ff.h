@@ -46,33 +46,103 @@ inline Fr sub_raw(const Fr& a, const Fr& b) {
     }
     return r;
 }
+// t (< 2r, with `hi` = the carry out of bit 256) reduced once: t - r if that does not borrow, else t.  Branch-free.
+inline Fr reduce_once(const Fr& t, uint64_t hi = 0) {
+    Fr d;
+    unsigned char brw = 0;
+    unsigned long long x;
+    brw = __builtin_usubll_overflow(t.l[0], FR_MOD.l[0], &x); d.l[0] = x;
+    for (int i = 1; i < 4; i++) {
+        unsigned long long y;
+        unsigned char b1 = __builtin_usubll_overflow(t.l[i], FR_MOD.l[i], &y);
+        unsigned char b2 = __builtin_usubll_overflow(y, (unsigned long long)brw, &x);
+        d.l[i] = x;
+        brw = b1 | b2;
+    }
+    const uint64_t keep = (uint64_t)0 - (uint64_t)(brw && !hi);      // all ones: t < r, keep t
+    Fr r;
+    for (int i = 0; i < 4; i++) r.l[i] = (t.l[i] & keep) | (d.l[i] & ~keep);
+    return r;
+}
 inline Fr add(const Fr& a, const Fr& b) {
     Fr t;
     u128 c = 0;
     for (int i = 0; i < 4; i++) { c += (u128)a.l[i] + b.l[i]; t.l[i] = (uint64_t)c; c >>= 64; }
-    return (c || geq(t, FR_MOD)) ? sub_raw(t, FR_MOD) : t;
+    return reduce_once(t, (uint64_t)c);
 }
 inline Fr sub(const Fr& a, const Fr& b) { return geq(a, b) ? sub_raw(a, b) : sub_raw(FR_MOD, sub_raw(b, a)); }
 inline Fr neg(const Fr& a) { return a.is_zero() ? a : sub_raw(FR_MOD, a); }
-inline Fr mul(const Fr& a, const Fr& b) {
-    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-    const uint64_t* p = FR_MOD.l;
-    for (int i = 0; i < 4; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4; j++) { c += (u128)a.l[j] * b.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-        c += t[4];
-        t[4] = (uint64_t)c;
-        t[5] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * FR_INV;
-        c = ((u128)m * p[0] + t[0]) >> 64;
-        for (int j = 1; j < 4; j++) { c += (u128)m * p[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-        c += t[4];
-        t[3] = (uint64_t)c;
-        t[4] = t[5] + (uint64_t)(c >> 64);
+// Montgomery product, CIOS with the "no-carry" shortcut (valid because the top limb of r is below 2^63 - 1: the
+// running sum never needs a sixth limb), fully unrolled: the transcript's Poseidon sponge is ~2 M products per proof
+// and is the only host arithmetic on the critical path.
+inline Fr mul_portable(const Fr& a, const Fr& b) {
+    const uint64_t q0 = FR_MOD.l[0], q1 = FR_MOD.l[1], q2 = FR_MOD.l[2], q3 = FR_MOD.l[3];
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define ZK_MONT_ROUND(bi)                                                             \
+    {                                                                                 \
+        u128 A = (u128)a.l[0] * (bi) + t0;                                            \
+        const uint64_t m = (uint64_t)A * FR_INV;                                      \
+        u128 C = (u128)m * q0 + (uint64_t)A;                                          \
+        A = (u128)a.l[1] * (bi) + t1 + (uint64_t)(A >> 64);                           \
+        C = (u128)m * q1 + (uint64_t)A + (uint64_t)(C >> 64);                         \
+        t0 = (uint64_t)C;                                                             \
+        A = (u128)a.l[2] * (bi) + t2 + (uint64_t)(A >> 64);                           \
+        C = (u128)m * q2 + (uint64_t)A + (uint64_t)(C >> 64);                         \
+        t1 = (uint64_t)C;                                                             \
+        A = (u128)a.l[3] * (bi) + t3 + (uint64_t)(A >> 64);                           \
+        C = (u128)m * q3 + (uint64_t)A + (uint64_t)(C >> 64);                         \
+        t2 = (uint64_t)C;                                                             \
+        t3 = (uint64_t)(C >> 64) + (uint64_t)(A >> 64);                               \
     }
-    Fr o = {{t[0], t[1], t[2], t[3]}};
-    return (t[4] || geq(o, FR_MOD)) ? sub_raw(o, FR_MOD) : o;
+    ZK_MONT_ROUND(b.l[0]) ZK_MONT_ROUND(b.l[1]) ZK_MONT_ROUND(b.l[2]) ZK_MONT_ROUND(b.l[3])
+#undef ZK_MONT_ROUND
+    Fr o = {{t0, t1, t2, t3}};
+    return reduce_once(o);
 }
+#if defined(__x86_64__) && defined(__GNUC__)
+// The same product with BMI2 / ADX (mulx + the two independent carry chains of adcx / adox): ~130 instructions instead
+// of the ~330 gcc makes of the portable form, i.e. ~3x the throughput.  Five accumulator registers rotate through the
+// four rounds (after a round's reduction the low limb is exactly zero and becomes the next round's top limb).
+#define ZK_MM_MULADD(src, off, T0, T1, T2, T3, A)                                        \
+    "xorl %%eax, %%eax\n\t"                                                              \
+    "mulxq " #off "+0(%[" #src "]), %%r13, %%r14\n\t adoxq %%r13, " T0 "\n\t adcxq %%r14, " T1 "\n\t"  \
+    "mulxq " #off "+8(%[" #src "]), %%r13, %%r14\n\t adoxq %%r13, " T1 "\n\t adcxq %%r14, " T2 "\n\t"  \
+    "mulxq " #off "+16(%[" #src "]), %%r13, %%r14\n\t adoxq %%r13, " T2 "\n\t adcxq %%r14, " T3 "\n\t" \
+    "mulxq " #off "+24(%[" #src "]), %%r13, %%r14\n\t adoxq %%r13, " T3 "\n\t adcxq %%r14, " A "\n\t"  \
+    "adoxq %%rax, " A "\n\t"
+#define ZK_MM_ROUND(boff, T0, T1, T2, T3, A)                                             \
+    "movq " #boff "(%[b]), %%rdx\n\t"                                                    \
+    ZK_MM_MULADD(a, 0, T0, T1, T2, T3, A)                                                \
+    "movq " T0 ", %%rdx\n\t imulq %[inv], %%rdx\n\t"                                     \
+    ZK_MM_MULADD(q, 0, T0, T1, T2, T3, A)
+inline Fr mul_adx(const Fr& a, const Fr& b) {
+    Fr o;
+    __asm__(
+        "xorl %%r8d, %%r8d\n\t xorl %%r9d, %%r9d\n\t xorl %%r10d, %%r10d\n\t xorl %%r11d, %%r11d\n\t xorl %%r12d, %%r12d\n\t"
+        ZK_MM_ROUND(0, "%%r8", "%%r9", "%%r10", "%%r11", "%%r12")
+        ZK_MM_ROUND(8, "%%r9", "%%r10", "%%r11", "%%r12", "%%r8")
+        ZK_MM_ROUND(16, "%%r10", "%%r11", "%%r12", "%%r8", "%%r9")
+        ZK_MM_ROUND(24, "%%r11", "%%r12", "%%r8", "%%r9", "%%r10")
+        // result in (r12, r8, r9, r10); subtract r once if that does not borrow
+        "movq %%r12, %%r13\n\t movq %%r8, %%r14\n\t movq %%r9, %%rax\n\t movq %%r10, %%rdx\n\t"
+        "subq 0(%[q]), %%r13\n\t sbbq 8(%[q]), %%r14\n\t sbbq 16(%[q]), %%rax\n\t sbbq 24(%[q]), %%rdx\n\t"
+        "cmovcq %%r12, %%r13\n\t cmovcq %%r8, %%r14\n\t cmovcq %%r9, %%rax\n\t cmovcq %%r10, %%rdx\n\t"
+        "movq %%r13, 0(%[o])\n\t movq %%r14, 8(%[o])\n\t movq %%rax, 16(%[o])\n\t movq %%rdx, 24(%[o])\n\t"
+        :
+        : [a] "r"(a.l), [b] "r"(b.l), [q] "r"(FR_MOD.l), [inv] "r"(FR_INV), [o] "r"(o.l)
+        : "rax", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "cc", "memory");
+    return o;
+}
+#undef ZK_MM_ROUND
+#undef ZK_MM_MULADD
+inline bool cpu_has_adx() {
+    static const bool ok = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx");
+    return ok;
+}
+inline Fr mul(const Fr& a, const Fr& b) { return cpu_has_adx() ? mul_adx(a, b) : mul_portable(a, b); }
+#else
+inline Fr mul(const Fr& a, const Fr& b) { return mul_portable(a, b); }
+#endif
 inline Fr sqr(const Fr& a) { return mul(a, a); }
 inline Fr to_mont(const Fr& canon) { return mul(canon, FR_R2); }
 inline Fr from_mont(const Fr& m) { Fr one = {{1, 0, 0, 0}}; return mul(m, one); }
@@ -104,22 +174,51 @@ inline Fr omega(uint32_t k) {   // generator of the 2^k-th roots of unity (Montg
 }
 
 // ---- Poseidon permutation (t = 5, full rounds 8, partial rounds 60, x^5) ---------------------
+// Optimised form (tables derived and checked against the plain form by gen_poseidon.py): the partial rounds add one
+// scalar and multiply by a sparse matrix -- 12 field products per partial round instead of 28, 1056 per permutation
+// instead of 2000.  `poseidon_permute_plain` is the textbook form over (RC, MDS); the CPU tests hold both against the
+// oracle (which is pinned by the published t = 3 / t = 2 vectors).
+inline const Fr& pc(const uint64_t (*tbl)[4], size_t i) { return *(const Fr*)tbl[i]; }
+inline Fr pow5(const Fr& x) { Fr x2 = sqr(x); return mul(sqr(x2), x); }
+inline void poseidon_mds(Fr s[POSEIDON_T], const uint64_t (*m)[4]) {
+    Fr n[POSEIDON_T];
+    for (int i = 0; i < POSEIDON_T; i++) {
+        Fr acc = mul(pc(m, i * POSEIDON_T), s[0]);
+        for (int j = 1; j < POSEIDON_T; j++) acc = add(acc, mul(pc(m, i * POSEIDON_T + j), s[j]));
+        n[i] = acc;
+    }
+    for (int i = 0; i < POSEIDON_T; i++) s[i] = n[i];
+}
 inline void poseidon_permute(Fr s[POSEIDON_T]) {
+    const int T = POSEIDON_T, half = POSEIDON_RF / 2;
+    for (int r = 0; r < half; r++) {
+        for (int i = 0; i < T; i++) s[i] = pow5(add(s[i], pc(POSEIDON_C_FIRST, r * T + i)));
+        poseidon_mds(s, POSEIDON_MDS);
+    }
+    for (int r = 0; r < POSEIDON_RP; r++) {
+        s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
+        if (r + 1 < POSEIDON_RP) {
+            const size_t b = (size_t)r * (2 * T - 1);
+            Fr n0 = mul(pc(POSEIDON_SPARSE, b), s[0]);
+            for (int j = 1; j < T; j++) n0 = add(n0, mul(pc(POSEIDON_SPARSE, b + j), s[j]));
+            for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
+            s[0] = n0;
+        } else {
+            poseidon_mds(s, POSEIDON_M_LAST);
+        }
+    }
+    for (int r = 0; r < half; r++) {
+        for (int i = 0; i < T; i++) s[i] = pow5(add(s[i], pc(POSEIDON_C_SECOND, r * T + i)));
+        poseidon_mds(s, POSEIDON_MDS);
+    }
+}
+inline void poseidon_permute_plain(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2, rounds = POSEIDON_RF + POSEIDON_RP;
     for (int r = 0; r < rounds; r++) {
-        for (int i = 0; i < T; i++) s[i] = add(s[i], *(const Fr*)POSEIDON_RC[r * T + i]);
-        bool full = r < half || r >= half + POSEIDON_RP;
-        for (int i = 0; i < (full ? T : 1); i++) {
-            Fr x2 = sqr(s[i]);
-            s[i] = mul(mul(x2, x2), s[i]);
-        }
-        Fr n[POSEIDON_T];
-        for (int i = 0; i < T; i++) {
-            Fr acc = FR_ZERO;
-            for (int j = 0; j < T; j++) acc = add(acc, mul(*(const Fr*)POSEIDON_MDS[i * T + j], s[j]));
-            n[i] = acc;
-        }
-        for (int i = 0; i < T; i++) s[i] = n[i];
+        for (int i = 0; i < T; i++) s[i] = add(s[i], pc(POSEIDON_RC, r * T + i));
+        const bool full = r < half || r >= half + POSEIDON_RP;
+        for (int i = 0; i < (full ? T : 1); i++) s[i] = pow5(s[i]);
+        poseidon_mds(s, POSEIDON_MDS);
     }
 }
 
@@ -201,14 +300,17 @@ inline Fr from_uniform_bytes(const uint8_t b[64]) {
 
 // ---- transcript ------------------------------------------------------------------------------
 // Two interchangeable Fiat-Shamir hashes over the same message sequence:
-//   BLAKE2B  (default) halo2's own `Blake2bWrite` / `Challenge255` shape: every absorbed item is fed
-//            to a running BLAKE2b-512 with a one-byte tag; a challenge is the digest of the state so
-//            far (tag 0 appended), reduced from 512 bits.  Microseconds per proof on the host.
-//   POSEIDON the hash family the reference reaches through snark-verifier's PoseidonTranscript
-//            (t = 5, rate 4, R_F = 8, R_P = 60): sponge over state[1..4]; a squeeze pads the buffer
-//            with a single 1, absorbs it rate-by-rate and returns state[1].  Points are absorbed as
-//            four Fr elements (low / high 128 bits of canonical x and y).  ~60 us per permutation on
-//            the host, i.e. tens of ms per proof -- selectable, not the default.
+//   POSEIDON (default; what the reference's `prove` runs: snark-verifier-sdk `gen_snark_shplonk` ->
+//            `PoseidonTranscript<NativeLoader>` over the PSE `poseidon` crate, t = 5, rate 4, R_F = 8, R_P = 60
+//            [UPSTREAM-RECALL, SURVEY.md App. C.2]): a sponge over state[1..4] starting from state[0] = 2^64
+//            (the crate's `State::default`); absorbed items queue up and a squeeze pads them with a single 1,
+//            absorbs them rate-by-rate (an exact multiple of the rate gets one extra block holding only the 1) and
+//            returns state[1].  Scalars are absorbed natively, points as two elements, x mod r and y mod r (the
+//            transcript's `fe_to_fe` of the affine coordinates).  ~1,700 permutations per config-1 proof (1,281 of
+//            them for the 5,121 public instances), on the host.
+//   BLAKE2B  halo2's own `Blake2bWrite` / `Challenge255` shape: every absorbed item is fed to a running
+//            BLAKE2b-512 with a one-byte tag; a challenge is the digest of the state so far (tag 0 appended),
+//            reduced from 512 bits.  Microseconds per proof; selectable (kind 0).
 // Every written item is also appended to the proof in canonical little-endian form (points
 // uncompressed, x || y, identity = 64 zero bytes), so the verifier replays the same sequence.
 enum TranscriptKind { TRANSCRIPT_BLAKE2B = 0, TRANSCRIPT_POSEIDON = 1 };
@@ -220,9 +322,10 @@ struct Transcript {
     std::vector<Fr> buf;
     std::vector<uint8_t> proof;
 
-    explicit Transcript(int kind_ = TRANSCRIPT_BLAKE2B) : kind(kind_) {
+    explicit Transcript(int kind_ = TRANSCRIPT_POSEIDON) : kind(kind_) {
         for (auto& s : state) s = FR_ZERO;
-        state[0] = from_u64(0x7a6b666865ULL);   // domain tag "zkfhe"
+        const Fr two64 = {{0, 1, 0, 0}};
+        state[0] = to_mont(two64);              // capacity element 2^64
         const char tag[] = "zkfhe-b200-transcript-v1";
         b2.update(tag, sizeof tag - 1);
     }
@@ -243,10 +346,10 @@ struct Transcript {
     void common_point(const uint64_t x_canon[4], const uint64_t y_canon[4]) {
         if (kind == TRANSCRIPT_POSEIDON) {
             const uint64_t* cs[2] = {x_canon, y_canon};
-            for (auto c : cs) {
-                Fr lo = {{c[0], c[1], 0, 0}}, hi = {{c[2], c[3], 0, 0}};
-                buf.push_back(to_mont(lo));
-                buf.push_back(to_mont(hi));
+            for (auto c : cs) {                 // Fq coordinate -> Fr: p < 2r, so one conditional subtraction
+                Fr v = {{c[0], c[1], c[2], c[3]}};
+                if (geq(v, FR_MOD)) v = sub_raw(v, FR_MOD);
+                buf.push_back(to_mont(v));
             }
             return;
         }

@@ -93,6 +93,50 @@ static std::string hex32(const uint64_t l[4]) {
     return b;
 }
 
+
+// Shared tail of keygen and of zkfhe_pk_import: everything that is a function of the layout numbers, the Lagrange
+// form of the fixed columns and their commitments -- coefficient and extended forms, the pinning JSON, the vk digest.
+static int pk_finalize(zkfhe_pk* pk) {
+    zkfhe_ctx* ctx = pk->ctx;
+    const uint32_t n = pk->n, k = pk->k;
+    const size_t fbytes = (size_t)pk->n_fixed * n * sizeof(fr_t);
+    ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_coeff, pk->fixed_lagrange, fbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_coeff, n, k, pk->n_fixed, 1, 0));
+    ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_ext, (uint64_t)n << EXT_SHIFT, k + EXT_SHIFT, pk->n_fixed, 0, 1));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    // ---- pinning (configs/<name>.json schema of the reference) and vk digest -----------------------------
+    pk->pinning_json =
+        "{\"params\":{\"degree\":" + std::to_string(k) + ",\"num_rlc_columns\":" + std::to_string(pk->n_rlc) +
+        ",\"num_range_advice\":[" + std::to_string(pk->n_gate0) + "," + std::to_string(pk->n_gate1) + ",0]" +
+        ",\"num_lookup_advice\":[0," + std::to_string(pk->n_lookup) + ",0],\"num_fixed\":1,\"unusable_rows\":" +
+        std::to_string(pk->unusable_rows) + ",\"keccak_rows_per_round\":50,\"lookup_bits\":" + std::to_string(pk->lookup_bits) +
+        "},\"break_points\":{\"gate\":[" + json_list(pk->cut[0].break_points) + "," + json_list(pk->cut[1].break_points) +
+        ",[]],\"rlc\":" + json_list(pk->cut[2].break_points) + "}}";
+    host::Transcript t(host::TRANSCRIPT_BLAKE2B);
+    const uint32_t shape[] = {k, pk->n_gate0, pk->n_gate1, pk->n_rlc, pk->n_lookup, pk->unusable_rows, pk->lookup_bits,
+                              (uint32_t)pk->instances, BLINDING_FACTORS, PERM_CHUNK};
+    for (uint32_t s : shape) t.common_scalar(host::from_u64(s));
+    for (const auto& cm : pk->fixed_commitments_canon) t.common_point(cm.data(), cm.data() + 4);
+    pk->vk_digest = t.squeeze();
+    return ZKFHE_OK;
+}
+
+// layout numbers that follow from the column cuts and the lookup count
+static void pk_derive_layout(zkfhe_pk* pk) {
+    pk->n_gate0 = (uint32_t)pk->cut[0].rows.size();
+    pk->n_gate1 = (uint32_t)pk->cut[1].rows.size();
+    pk->n_rlc = (uint32_t)pk->cut[2].rows.size();
+    pk->n_lookup = (uint32_t)((pk->lookups + pk->max_rows - 1) / pk->max_rows);
+    pk->n_advice = pk->n_gate0 + pk->n_gate1 + pk->n_rlc + pk->n_lookup;
+    pk->n_perm = pk->n_advice + 2;
+    pk->n_chunks = (pk->n_perm + PERM_CHUNK - 1) / PERM_CHUNK;
+    const uint32_t n_gate = pk->n_gate0 + pk->n_gate1, n_sel = n_gate + pk->n_rlc;
+    pk->fx_qgate = 0; pk->fx_qrlc = n_gate; pk->fx_const = n_sel; pk->fx_table = n_sel + 1;
+    pk->fx_l0 = n_sel + 2; pk->fx_llast = n_sel + 3; pk->fx_lactive = n_sel + 4; pk->fx_sigma = n_sel + 5;
+    pk->n_fixed = pk->fx_sigma + pk->n_perm;
+}
+
 }  // namespace zkfhe
 
 extern "C" {
@@ -159,17 +203,8 @@ int zkfhe_keygen(zkfhe_witness* w, uint32_t k, uint32_t unusable_rows, zkfhe_pk*
     cut_context(flags[0].data(), flags[0].size(), pk->max_rows, 4, pk->cut[0]);
     cut_context(flags[1].data(), flags[1].size(), pk->max_rows, 4, pk->cut[1]);
     cut_context(flags[2].data(), flags[2].size(), pk->max_rows, 3, pk->cut[2]);
-    pk->n_gate0 = (uint32_t)pk->cut[0].rows.size();
-    pk->n_gate1 = (uint32_t)pk->cut[1].rows.size();
-    pk->n_rlc = (uint32_t)pk->cut[2].rows.size();
-    pk->n_lookup = (uint32_t)((pk->lookups + pk->max_rows - 1) / pk->max_rows);
-    pk->n_advice = pk->n_gate0 + pk->n_gate1 + pk->n_rlc + pk->n_lookup;
-    pk->n_perm = pk->n_advice + 2;
-    pk->n_chunks = (pk->n_perm + PERM_CHUNK - 1) / PERM_CHUNK;
+    pk_derive_layout(pk);
     const uint32_t n_gate = pk->n_gate0 + pk->n_gate1, n_sel = n_gate + pk->n_rlc;
-    pk->fx_qgate = 0; pk->fx_qrlc = n_gate; pk->fx_const = n_sel; pk->fx_table = n_sel + 1;
-    pk->fx_l0 = n_sel + 2; pk->fx_llast = n_sel + 3; pk->fx_lactive = n_sel + 4; pk->fx_sigma = n_sel + 5;
-    pk->n_fixed = pk->fx_sigma + pk->n_perm;
     const uint32_t col_base[3] = {0, pk->n_gate0, n_gate};
     const uint32_t lookup_base = n_gate + pk->n_rlc;
     const uint32_t perm_const = pk->n_advice, perm_inst = pk->n_advice + 1;
@@ -204,6 +239,9 @@ int zkfhe_keygen(zkfhe_witness* w, uint32_t k, uint32_t unusable_rows, zkfhe_pk*
             uf.unite(pos(col_base[c] + (uint32_t)j, cut.break_points[j]), pos(col_base[c] + (uint32_t)j + 1, 0));
         for (uint64_t off = 0; off < flags[c].size(); off++) {
             const uint8_t f = flags[c][off];
+            if (f & META_COPY_CONFLICT)
+                return fail(ctx, ZKFHE_ERR_STATE, "keygen: cell %llu of context %d was given two different copy sources "
+                            "(an equality constraint would be dropped)", (unsigned long long)off, c);
             uint32_t col, row;
             locate(cell_id(c, off), col, row);
             if (f & META_SELECTOR) {
@@ -286,25 +324,133 @@ int zkfhe_keygen(zkfhe_witness* w, uint32_t k, uint32_t unusable_rows, zkfhe_pk*
     pk->fixed_commitments_canon.resize(pk->n_fixed);
     ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_commitments_canon.data(), d_comm, (size_t)pk->n_fixed * sizeof(g1_affine),
                                  cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_coeff, pk->fixed_lagrange, fbytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_coeff, n, k, pk->n_fixed, 1, 0));
-    ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_ext, (uint64_t)n << EXT_SHIFT, k + EXT_SHIFT, pk->n_fixed, 0, 1));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_TRY(pk_finalize(pk));
+    guard.p = nullptr;
+    *out = pk;
+    return ZKFHE_OK;
+}
 
-    // ---- pinning (configs/<name>.json schema of the reference) and vk digest -----------------------------
-    pk->pinning_json =
-        "{\"params\":{\"degree\":" + std::to_string(k) + ",\"num_rlc_columns\":" + std::to_string(pk->n_rlc) +
-        ",\"num_range_advice\":[" + std::to_string(pk->n_gate0) + "," + std::to_string(pk->n_gate1) + ",0]" +
-        ",\"num_lookup_advice\":[0," + std::to_string(pk->n_lookup) + ",0],\"num_fixed\":1,\"unusable_rows\":" +
-        std::to_string(unusable_rows) + ",\"keccak_rows_per_round\":50,\"lookup_bits\":" + std::to_string(pk->lookup_bits) +
-        "},\"break_points\":{\"gate\":[" + json_list(pk->cut[0].break_points) + "," + json_list(pk->cut[1].break_points) +
-        ",[]],\"rlc\":" + json_list(pk->cut[2].break_points) + "}}";
-    host::Transcript t;
-    const uint32_t shape[] = {k, pk->n_gate0, pk->n_gate1, pk->n_rlc, pk->n_lookup, unusable_rows, pk->lookup_bits,
-                              (uint32_t)pk->instances, BLINDING_FACTORS, PERM_CHUNK};
-    for (uint32_t s : shape) t.common_scalar(host::from_u64(s));
-    for (const auto& cm : pk->fixed_commitments_canon) t.common_point(cm.data(), cm.data() + 4);
-    pk->vk_digest = t.squeeze();
+
+// ---- data/<name>.pk: the proving key as a file (README.md:38 -- keygen once, prove many) -----------------------
+// "ZKFHEPK1" | u32 k, unusable_rows, lookup_bits, reserved | u64 cells[3], lookups, instances |
+// 3 x { u32 columns; u32 break_points[columns-1]; u64 start[columns]; u32 rows[columns] } | u64 public_cells[instances] |
+// fixed commitments (n_fixed x 64 B, Montgomery affine) | fixed columns in Lagrange form (n_fixed x n x 32 B, Montgomery).
+// Everything else (coefficient / extended forms, sigma-independent tables, the digest) is recomputed on import.
+static const char PK_MAGIC[8] = {'Z', 'K', 'F', 'H', 'E', 'P', 'K', '1'};
+
+int zkfhe_pk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed) {
+    if (!pk) return ZKFHE_ERR_ARG;
+    zkfhe_ctx* ctx = pk->ctx;
+    size_t need = 8 + 16 + 40;
+    for (int c = 0; c < 3; c++) {
+        const size_t cols = pk->cut[c].rows.size();
+        need += 4 + (cols ? (cols - 1) * 4 : 0) + cols * 8 + cols * 4;
+    }
+    need += pk->public_cells.size() * 8 + (size_t)pk->n_fixed * 64 + (size_t)pk->n_fixed * pk->n * 32;
+    if (needed) *needed = need;
+    if (!buf) return ZKFHE_OK;
+    if (cap < need) return fail(ctx, ZKFHE_ERR_ARG, "pk_export: buffer of %zu bytes, %zu needed", cap, need);
+    uint8_t* p = buf;
+    auto put = [&](const void* src, size_t len) { memcpy(p, src, len); p += len; };
+    put(PK_MAGIC, 8);
+    const uint32_t head[4] = {pk->k, pk->unusable_rows, pk->lookup_bits, 0};
+    put(head, 16);
+    const uint64_t counts[5] = {pk->cells[0], pk->cells[1], pk->cells[2], pk->lookups, pk->instances};
+    put(counts, 40);
+    for (int c = 0; c < 3; c++) {
+        const uint32_t cols = (uint32_t)pk->cut[c].rows.size();
+        put(&cols, 4);
+        if (cols) put(pk->cut[c].break_points.data(), (size_t)(cols - 1) * 4);
+        put(pk->cut[c].start.data(), (size_t)cols * 8);
+        put(pk->cut[c].rows.data(), (size_t)cols * 4);
+    }
+    put(pk->public_cells.data(), pk->public_cells.size() * 8);
+    put(pk->fixed_commitments.data(), (size_t)pk->n_fixed * 64);
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaMemcpyAsync(p, pk->fixed_lagrange, (size_t)pk->n_fixed * pk->n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKFHE_OK;
+}
+
+int zkfhe_pk_import(zkfhe_ctx* ctx, const uint8_t* buf, size_t len, zkfhe_pk** out) {
+    if (!ctx || !buf || !out) return ZKFHE_ERR_ARG;
+    const uint8_t* p = buf;
+    const uint8_t* end = buf + len;
+    bool short_read = false;
+    auto get = [&](void* dst, size_t m) {
+        if ((size_t)(end - p) < m) { short_read = true; return; }
+        memcpy(dst, p, m);
+        p += m;
+    };
+    char magic[8] = {0};
+    uint32_t head[4] = {0, 0, 0, 0};
+    uint64_t counts[5] = {0, 0, 0, 0, 0};
+    get(magic, 8); get(head, 16); get(counts, 40);
+    if (short_read || memcmp(magic, PK_MAGIC, 8)) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: not a zkfhe proving key");
+    const uint32_t k = head[0];
+    if (k < 4 || k > 20) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: k=%u out of range", k);
+    if (ctx->srs_k != k) return fail(ctx, ZKFHE_ERR_STATE, "pk_import: SRS for k=%u is not loaded (have k=%u)", k, ctx->srs_k);
+    const uint32_t n = 1u << k;
+    if (head[1] < BLINDING_FACTORS + 3 || head[1] >= n / 2 || head[2] == 0 || head[2] > 12)
+        return fail(ctx, ZKFHE_ERR_ARG, "pk_import: inconsistent header");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    zkfhe_pk* pk = new (std::nothrow) zkfhe_pk();
+    if (!pk) return fail(ctx, ZKFHE_ERR_CUDA, "out of host memory");
+    struct Guard { zkfhe_pk* p; ~Guard() { if (p) zkfhe_pk_free(p); } } guard{pk};
+    pk->ctx = ctx;
+    pk->k = k; pk->n = n; pk->unusable_rows = head[1]; pk->lookup_bits = head[2];
+    pk->max_rows = n - pk->unusable_rows;
+    pk->usable = n - BLINDING_FACTORS - 1;
+    for (int c = 0; c < 3; c++) pk->cells[c] = counts[c];
+    pk->lookups = counts[3];
+    pk->instances = counts[4];
+    for (int c = 0; c < 3; c++) {
+        uint32_t cols = 0;
+        get(&cols, 4);
+        if (short_read || cols > 65536) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: truncated or corrupt column table");
+        pk->cut[c].break_points.resize(cols ? cols - 1 : 0);
+        pk->cut[c].start.resize(cols);
+        pk->cut[c].rows.resize(cols);
+        if (cols) get(pk->cut[c].break_points.data(), (size_t)(cols - 1) * 4);
+        get(pk->cut[c].start.data(), (size_t)cols * 8);
+        get(pk->cut[c].rows.data(), (size_t)cols * 4);
+        uint64_t covered = 0;
+        for (uint32_t j = 0; j < cols && !short_read; j++) {
+            if (pk->cut[c].rows[j] > pk->max_rows || pk->cut[c].start[j] + pk->cut[c].rows[j] > pk->cells[c])
+                return fail(ctx, ZKFHE_ERR_ARG, "pk_import: column %u of context %d lies outside its context", j, c);
+            covered = pk->cut[c].start[j] + pk->cut[c].rows[j];
+        }
+        if (!short_read && covered != pk->cells[c]) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: the columns of context %d do not cover it", c);
+    }
+    if (short_read || pk->instances > pk->usable) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: truncated or corrupt key");
+    pk->public_cells.resize(pk->instances);
+    get(pk->public_cells.data(), pk->instances * 8);
+    for (uint64_t id : pk->public_cells)
+        if (id == CELL_NONE || cell_ctx(id) > 2 || cell_off(id) >= pk->cells[cell_ctx(id)])
+            return fail(ctx, ZKFHE_ERR_ARG, "pk_import: a public cell lies outside the witness");
+    pk_derive_layout(pk);
+    pk->fixed_commitments.resize(pk->n_fixed);
+    get(pk->fixed_commitments.data(), (size_t)pk->n_fixed * 64);
+    const size_t fbytes = (size_t)pk->n_fixed * n * sizeof(fr_t);
+    if (short_read || (size_t)(end - p) != fbytes) return fail(ctx, ZKFHE_ERR_ARG, "pk_import: length mismatch (%zu bytes of fixed columns expected)", fbytes);
+    ZK_CUDA(ctx, cudaMalloc(&pk->fixed_lagrange, fbytes));
+    ZK_CUDA(ctx, cudaMalloc(&pk->fixed_coeff, fbytes));
+    ZK_CUDA(ctx, cudaMalloc(&pk->fixed_ext, fbytes << EXT_SHIFT));
+    ZK_CUDA(ctx, cudaMalloc(&pk->delta_pow, (size_t)pk->n_perm * sizeof(fr_t)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_lagrange, p, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<host::Fr> dpow(pk->n_perm);
+    {
+        host::Fr d = host::to_mont(host::FR_DELTA_CANON), acc = host::FR_ONE;
+        for (uint32_t c = 0; c < pk->n_perm; c++) { dpow[c] = acc; acc = host::mul(acc, d); }
+    }
+    ZK_CUDA(ctx, cudaMemcpyAsync(pk->delta_pow, dpow.data(), dpow.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    g1_affine* d_comm;
+    ZK_TRY(ws_get(ctx, "kg_comm", (size_t)pk->n_fixed * sizeof(g1_affine), (void**)&d_comm));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_comm, pk->fixed_commitments.data(), (size_t)pk->n_fixed * 64, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(points_to_canonical(ctx, d_comm, pk->n_fixed));
+    pk->fixed_commitments_canon.resize(pk->n_fixed);
+    ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_commitments_canon.data(), d_comm, (size_t)pk->n_fixed * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_TRY(pk_finalize(pk));      // synchronises: the host buffers above are complete
     guard.p = nullptr;
     *out = pk;
     return ZKFHE_OK;

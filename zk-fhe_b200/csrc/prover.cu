@@ -458,6 +458,7 @@ __global__ void k_axpy3(const fr_t* h, uint32_t n, fr_t s1, fr_t s2, fr_t* out) 
     fe_store(out + row, add(fe_load(h + row), add(mul(s1, fe_load(h + n + row)), mul(s2, fe_load(h + 2 * (uint64_t)n + row)))));
 }
 __global__ void k_sub_const0(fr_t* p, fr_t c) { fe_store(p, sub(fe_load(p), c)); }
+__global__ void k_status_clear_bits(uint32_t* status, uint32_t bits) { atomicAnd(status, ~bits); }
 
 }  // namespace zkfhe
 
@@ -677,6 +678,8 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     {
         ZK_TRY(fill_random(pr, 0, 2 * pk->n_lookup * nb));
         const uint32_t T = 1u << pk->lookup_bits;
+        // process-wide attribute: always the maximum any admitted lookup_bits (<= 12) can need (3 * 4096 words)
+        ZK_CUDA(ctx, cudaFuncSetAttribute(k_lookup_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
         k_lookup_permute<<<pk->n_lookup, 1024, 3 * T * 4, ctx->stream>>>(
             pr->P + (size_t)pr->lookup_adv_base * n, n, pr->P + (size_t)pr->ap_base * n, n, n, usable, T, pr->blind, status);
         ZK_CHECK_LAUNCH(ctx);
@@ -685,9 +688,14 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_CUDA(ctx, cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
         ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (st & (1u << 6)) {
-            ZK_CUDA(ctx, cudaMemsetAsync(status, 0, 4, ctx->stream));
+            k_status_clear_bits<<<1, 1, 0, ctx->stream>>>(status, 1u << 6);      // other recorded asserts stay for zkfhe_status
+            ZK_CHECK_LAUNCH(ctx);
             return fail(ctx, ZKFHE_ERR_UNSATISFIED, "prove: a lookup cell is outside the table [0, 2^%u)", pk->lookup_bits);
         }
+        // data-dependent reference asserts recorded by the phase-1 chip kernels (src/poly.rs:28,51,158,164; the
+        // emitter / layout-model check): a proof must not be produced from a witness that tripped one
+        if (st & 0xffffu) return fail(ctx, ZKFHE_ERR_ASSERT, "prove: the witness kernels recorded a failed assertion (status 0x%x); "
+                                      "zkfhe_status has the message", st & 0xffffu);
     }
     pr->mark(2);
     pr->beta = pr->tr.squeeze();

@@ -167,9 +167,15 @@ int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t
         return fail(ctx, ZKFHE_ERR_ARG, "verify: unknown transcript kind %d", transcript_kind);
     const uint32_t k = h.k, n = 1u << k, usable = h.usable, n_gate = h.n_gate0 + h.n_gate1, n_sel = n_gate + h.n_rlc;
     const uint32_t fx_qgate = 0, fx_qrlc = n_gate, fx_const = n_sel, fx_table = n_sel + 1, fx_l0 = n_sel + 2, fx_sigma = n_sel + 5;
-    if (k < 4 || k > 24 || h.n_fixed != fx_sigma + h.n_perm || h.n_advice != n_sel + h.n_lookup || usable + 1 >= n ||
-        h.n_chunks == 0 || h.n_chunks * PERM_CHUNK < h.n_perm || h.n_perm != h.n_advice + 2 || h.instances > usable)
+    if (k < 4 || k > 24 || h.n_fixed != fx_sigma + h.n_perm || h.n_advice != n_sel + h.n_lookup ||
+        h.n_perm != h.n_advice + 2 || h.instances > usable)
         return fail(ctx, ZKFHE_ERR_ARG, "verify: inconsistent verifying key");
+    // `usable` and `n_chunks` are not free parameters (and not part of the digest): the prover fixes
+    // usable = n - BLINDING_FACTORS - 1 and n_chunks = ceil(n_perm / PERM_CHUNK); a key that says otherwise
+    // would move l_last / l_active and the rotation w^usable without changing the digest
+    if (usable != n - BLINDING_FACTORS - 1 || h.n_chunks != (h.n_perm + PERM_CHUNK - 1) / PERM_CHUNK)
+        return fail(ctx, ZKFHE_ERR_ARG, "verify: verifying key carries usable_rows = %u / n_chunks = %u, the layout implies %u / %u",
+                    usable, h.n_chunks, n - BLINDING_FACTORS - 1, (h.n_perm + PERM_CHUNK - 1) / PERM_CHUNK);
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<Point> fixed_cm(h.n_fixed);
     for (uint32_t f = 0; f < h.n_fixed; f++) memcpy(fixed_cm[f].c, vk + sizeof h + 64 * (size_t)f, 64);
@@ -179,7 +185,7 @@ int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t
         // vk digest, exactly as keygen hashes it
         Fr digest;
         {
-            host::Transcript t;
+            host::Transcript t(host::TRANSCRIPT_BLAKE2B);     // the key digest is always BLAKE2b (keygen.cu pk_finalize)
             const uint32_t shape[] = {k, h.n_gate0, h.n_gate1, h.n_rlc, h.n_lookup, h.unusable_rows, h.lookup_bits,
                                       h.instances, BLINDING_FACTORS, PERM_CHUNK};
             for (uint32_t s : shape) t.common_scalar(host::from_u64(s));

@@ -743,6 +743,7 @@ __global__ void k_mock_cells(MockBases B, uint32_t ctx_id, uint64_t n, const uin
     fr_t v = fe_load(a + i);
     if ((f & META_ASSERT_ZERO) && !is_zero(v)) bad = true;
     if ((f & META_ASSERT_ONE) && !eq(v, fe_one<FR>())) bad = true;
+    if (f & META_COPY_CONFLICT) bad = true;          // a second copy source was dropped: the cell is under-constrained
     uint64_t c = copy[i];
     if (c != CELL_NONE && !eq(v, fe_load(B.adv[cell_ctx(c)] + cell_off(c)))) bad = true;
     if (bad) {

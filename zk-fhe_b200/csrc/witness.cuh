@@ -26,6 +26,7 @@ static constexpr uint8_t META_SELECTOR = 1;   // a gate starts at this cell
 static constexpr uint8_t META_CONSTANT = 2;   // Constant(c) cell: constrained to the fixed constant equal to its value
 static constexpr uint8_t META_ASSERT_ZERO = 4;   // gate.assert_is_const(cell, 0)
 static constexpr uint8_t META_ASSERT_ONE = 8;    // gate.assert_is_const(cell, 1)
+static constexpr uint8_t META_COPY_CONFLICT = 16;   // internal: a second, different copy source was requested for this cell
 
 // A value together with the cell that holds it (CELL_NONE for a fresh witness / constant).
 struct Val {
@@ -74,7 +75,9 @@ struct Emit {
     }
     // extra equality between an already emitted cell of this coefficient (`back` behind the cursor) and `to`
     __device__ __forceinline__ void equal_at(uint32_t back, uint64_t to) {
-        if (flags && copy[na - back] == CELL_NONE) copy[na - back] = to;
+        if (!flags) return;
+        if (copy[na - back] == CELL_NONE) copy[na - back] = to;
+        else if (copy[na - back] != to) flags[na - back] |= META_COPY_CONFLICT;   // one copy slot per cell: keygen / mock refuse
     }
     // gate.assert_is_const on the cell `back` behind the cursor (value 0 or 1)
     __device__ __forceinline__ void assert_const_at(uint32_t back, bool one) {

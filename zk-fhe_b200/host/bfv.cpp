@@ -9,9 +9,14 @@
 // <data-path>/<name>.snark and prints the proving time.
 // <data-path>/<name>.snark (public instances + proof) and prints the proving time, keygen also writes
 // <data-path>/<name>.vk, and verify reads the two files back and prints the verification time.
-// Differences, stated plainly: the proving key is rebuilt in-process (no .pk file); the SRS is
-// the deterministic *test* setup every time (halo2-scaffold's gen_srs falls back to one too); the
-// proof / vk / snark formats are this implementation's own.
+// keygen also writes <data-path>/<name>.pk, which prove reads back (README.md:38: keygen once, prove many).
+//
+// Commitment key: `--srs <file>` (default params/kzg_bn254_<k>.srs, the path halo2-scaffold's gen_srs reads) holds
+// g, g_lagrange and [tau]_2; `bfv -k <k> setup` writes one from a trapdoor drawn from the OS and then forgotten.
+// Without a file the tool REFUSES to run unless `--insecure-test-srs` is given: that flag uses a fixed public trapdoor
+// (anyone can forge proofs against it) and exists for tests and benchmarks only.  The reference falls back to such a
+// test setup silently; this tool makes the caller say so.
+// The proof / pk / vk / snark / srs formats are this implementation's own.
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -86,9 +91,40 @@ static void fr_mont_from_u64(uint64_t v, uint8_t out[32]) {
     memcpy(out, a, 32);
 }
 
+static std::string slurp(const std::string& path, const char* hint) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error(ZKFHE_ERR_ARG, "cannot open " + path + hint);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// params file: "ZKFHESRS" | u32 k | u32 reserved | g (n x 64) | g_lagrange (n x 64) | [tau]_2 (128); Montgomery coordinates
+struct Srs { uint32_t k = 0; std::string g, gl; uint8_t s_g2[128]; };
+static Srs read_srs(const std::string& path, uint32_t k) {
+    const std::string raw = slurp(path, " (run `bfv -k <k> setup` first, or pass --srs <file> / --insecure-test-srs)");
+    const size_t n = (size_t)1 << k;
+    if (raw.size() != 16 + 128 * n + 128 || memcmp(raw.data(), "ZKFHESRS", 8)) throw Error(ZKFHE_ERR_ARG, path + " is not a zkfhe params file for this k");
+    Srs s;
+    memcpy(&s.k, raw.data() + 8, 4);
+    if (s.k != k) throw Error(ZKFHE_ERR_ARG, path + " holds parameters for another k");
+    s.g = raw.substr(16, 64 * n);
+    s.gl = raw.substr(16 + 64 * n, 64 * n);
+    memcpy(s.s_g2, raw.data() + 16 + 128 * n, 128);
+    return s;
+}
+
+static void os_random(uint8_t* out, size_t len) {
+    std::ifstream ur("/dev/urandom", std::ios::binary);
+    ur.read((char*)out, (std::streamsize)len);
+    if (!ur.good() || (size_t)ur.gcount() != len) throw Error(ZKFHE_ERR_STATE, "cannot read " + std::to_string(len) + " bytes from /dev/urandom");
+}
+
 int main(int argc, char** argv) {
-    std::string name = "bfv", input, config_path = "configs", data_path = "data", cmd;
+    std::string name = "bfv", input, config_path = "configs", data_path = "data", cmd, srs_path;
     uint32_t k = 13, unusable = 109;
+    int transcript = host::TRANSCRIPT_POSEIDON;
+    bool insecure_srs = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -98,34 +134,75 @@ int main(int argc, char** argv) {
         else if (a == "--config-path") config_path = next();
         else if (a == "--data-path") data_path = next();
         else if (a == "--unusable-rows") unusable = (uint32_t)std::stoul(next());
-        else if (a == "mock" || a == "keygen" || a == "prove" || a == "verify") cmd = a;
+        else if (a == "--srs") srs_path = next();
+        else if (a == "--insecure-test-srs") insecure_srs = true;
+        else if (a == "--transcript") { std::string t = next(); transcript = t == "blake2b" ? host::TRANSCRIPT_BLAKE2B : host::TRANSCRIPT_POSEIDON; }
+        else if (a == "mock" || a == "keygen" || a == "prove" || a == "verify" || a == "setup") cmd = a;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
-    if (cmd.empty() || input.empty()) {
-        fprintf(stderr, "usage: bfv --name <name> -k <degree> --input <file under data/> {mock|keygen|prove|verify}\n");
+    if (cmd.empty() || (input.empty() && cmd != "setup" && cmd != "verify")) {
+        fprintf(stderr, "usage: bfv --name <name> -k <degree> --input <file under data/> {mock|keygen|prove|verify}\n"
+                        "       bfv -k <degree> [--srs <file>] setup\n"
+                        "       options: --srs <file> | --insecure-test-srs, --config-path, --data-path, --unusable-rows, --transcript poseidon|blake2b\n");
         return 2;
     }
+    if (srs_path.empty()) srs_path = "params/kzg_bn254_" + std::to_string(k) + ".srs";
     try {
-        uint8_t tau[32];
-        fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau);              // deterministic TEST setup
+        uint8_t s_g2[128];
+        // the commitment key for keygen / prove (loaded on the device) and [tau]_2 for verify
+        auto load_srs = [&](Device* dev) {
+            if (insecure_srs) {
+                fprintf(stderr, "WARNING: --insecure-test-srs: the KZG trapdoor is a fixed PUBLIC constant; proofs against this key can be "
+                                "forged by anyone.  Tests and benchmarks only.\n");
+                uint8_t tau[32];
+                fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau);
+                if (dev) dev->check(zkfhe_srs_setup(dev->raw(), k, tau, nullptr, nullptr));
+                if (zkfhe_srs_g2(tau, s_g2) != ZKFHE_OK) throw Error(ZKFHE_ERR_ARG, "srs_g2 failed");
+                return;
+            }
+            Srs srs = read_srs(srs_path, k);
+            if (dev) dev->check(zkfhe_load_srs(dev->raw(), k, (const uint8_t*)srs.g.data(), (const uint8_t*)srs.gl.data()));
+            memcpy(s_g2, srs.s_g2, 128);
+        };
+        if (cmd == "setup") {
+            // halo2 `ParamsKZG::setup` shape from a trapdoor that never leaves this function.  Still a single-party
+            // setup: whoever runs it could have kept tau.  Use a ceremony transcript for anything real.
+            uint8_t seed[64], tau[32];
+            if (insecure_srs) { fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau); }
+            else {
+                os_random(seed, 64);
+                host::Fr t = host::from_uniform_bytes(seed);
+                memcpy(tau, t.l, 32);
+            }
+            Device dev(0);
+            const size_t n = (size_t)1 << k;
+            std::string g(64 * n, '\0'), gl(64 * n, '\0');
+            dev.check(zkfhe_srs_setup(dev.raw(), k, tau, (uint8_t*)&g[0], (uint8_t*)&gl[0]));
+            if (zkfhe_srs_g2(tau, s_g2) != ZKFHE_OK) throw Error(ZKFHE_ERR_ARG, "srs_g2 failed");
+            memset(tau, 0, sizeof tau);
+            memset(seed, 0, sizeof seed);
+            std::ofstream out(srs_path, std::ios::binary);
+            if (!out) throw Error(ZKFHE_ERR_ARG, "cannot write " + srs_path + " (does the directory exist?)");
+            const uint32_t head[2] = {k, 0};
+            out.write("ZKFHESRS", 8);
+            out.write((const char*)head, 8);
+            out.write(g.data(), (std::streamsize)g.size());
+            out.write(gl.data(), (std::streamsize)gl.size());
+            out.write((const char*)s_g2, 128);
+            printf("setup: wrote %s (k = %u, %zu bytes)\n", srs_path.c_str(), k, (size_t)(16 + 128 * n + 128));
+            return 0;
+        }
         if (cmd == "verify") {
             // reference README.md:48-54: reads the .vk written by keygen and the .snark written by prove
-            auto slurp = [](const std::string& path) {
-                std::ifstream f(path, std::ios::binary);
-                if (!f) throw Error(ZKFHE_ERR_ARG, "cannot open " + path + " (run keygen / prove first)");
-                std::stringstream ss;
-                ss << f.rdbuf();
-                return ss.str();
-            };
-            const std::string vk = slurp(data_path + "/" + name + ".vk"), snark = slurp(data_path + "/" + name + ".snark");
+            const std::string vk = slurp(data_path + "/" + name + ".vk", " (run keygen first)");
+            const std::string snark = slurp(data_path + "/" + name + ".snark", " (run prove first)");
             if (snark.size() < 16 || memcmp(snark.data(), "ZKFHESN1", 8)) throw Error(ZKFHE_ERR_ARG, "not a zkfhe snark file");
             uint32_t n_inst, kind;
             memcpy(&n_inst, snark.data() + 8, 4);
             memcpy(&kind, snark.data() + 12, 4);
             if (snark.size() < 16 + 32 * (size_t)n_inst) throw Error(ZKFHE_ERR_ARG, "snark file truncated");
             Device dev(0);
-            uint8_t s_g2[128];
-            dev.check(zkfhe_srs_g2(tau, s_g2));
+            load_srs(nullptr);
             int ok = 0;
             auto t0 = std::chrono::steady_clock::now();
             dev.check(zkfhe_verify(dev.raw(), (const uint8_t*)vk.data(), vk.size(), (const uint8_t*)snark.data() + 16, n_inst,
@@ -152,46 +229,56 @@ int main(int argc, char** argv) {
             printf("Mock prover: all constraints satisfied\n");
             return 0;
         }
-        dev.check(zkfhe_srs_setup(dev.raw(), k, tau, nullptr, nullptr));
-        // keygen always runs on an input of the same shape with all-zero values (README.md:31-36)
-        CircuitInput zeros;
-        for (auto& kv : in) zeros[kv.first] = std::vector<std::string>(kv.second.size(), "0");
-        BfvCircuit kg(dev, BfvParams(), 8, /*record=*/true);
-        kg.phase0(cmd == "keygen" ? in : zeros);
-        fr_mont_from_u64(1, gamma);
-        kg.phase1(gamma);
-        zkfhe_pk* pk = nullptr;
-        dev.check(zkfhe_keygen(kg.builder().raw(), k, unusable, &pk));
-        size_t need = 0;
-        zkfhe_pk_pinning_json(pk, nullptr, 0, &need);
-        std::string pin(need, '\0');
-        zkfhe_pk_pinning_json(pk, &pin[0], need, nullptr);
-        pin.resize(need - 1);
+        load_srs(&dev);
+        const std::string pk_path = data_path + "/" + name + ".pk";
         if (cmd == "keygen") {
+            // README.md:28-38: the circuit is synthesised on the given input (bfv_empty.in) in recording mode
+            BfvCircuit kg(dev, BfvParams(), 8, /*record=*/true);
+            kg.phase0(in);
+            fr_mont_from_u64(1, gamma);
+            kg.phase1(gamma);
+            zkfhe_pk* pk = nullptr;
+            dev.check(zkfhe_keygen(kg.builder().raw(), k, unusable, &pk));
+            size_t need = 0;
+            zkfhe_pk_pinning_json(pk, nullptr, 0, &need);
+            std::string pin(need, '\0');
+            zkfhe_pk_pinning_json(pk, &pin[0], need, nullptr);
+            pin.resize(need - 1);
             std::ofstream(config_path + "/" + name + ".json") << pin << "\n";
-            size_t vk_len = 0;
+            size_t vk_len = 0, pk_len = 0;
             dev.check(zkfhe_vk_export(pk, nullptr, 0, &vk_len));
             std::string vk(vk_len, '\0');
             dev.check(zkfhe_vk_export(pk, (uint8_t*)&vk[0], vk_len, nullptr));
             std::ofstream(data_path + "/" + name + ".vk", std::ios::binary).write(vk.data(), (std::streamsize)vk.size());
-            printf("keygen: wrote %s/%s.json and %s/%s.vk\n", config_path.c_str(), name.c_str(), data_path.c_str(), name.c_str());
+            dev.check(zkfhe_pk_export(pk, nullptr, 0, &pk_len));
+            std::string pkb(pk_len, '\0');
+            dev.check(zkfhe_pk_export(pk, (uint8_t*)&pkb[0], pk_len, nullptr));
+            std::ofstream(pk_path, std::ios::binary).write(pkb.data(), (std::streamsize)pkb.size());
+            printf("keygen: wrote %s/%s.json, %s/%s.vk and %s (%zu bytes)\n", config_path.c_str(), name.c_str(), data_path.c_str(),
+                   name.c_str(), pk_path.c_str(), pk_len);
             zkfhe_pk_free(pk);
             return 0;
         }
-        // prove (twice: the first pass also pays one-time device allocations; both times are printed)
+        // prove: reads the proving key keygen wrote (README.md:38)
+        zkfhe_pk* pk = nullptr;
+        {
+            const std::string pkb = slurp(pk_path, " (run keygen first)");
+            auto t0 = std::chrono::steady_clock::now();
+            dev.check(zkfhe_pk_import(dev.raw(), (const uint8_t*)pkb.data(), pkb.size(), &pk));
+            printf("Proving key loaded in %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+        // twice: the first pass also pays one-time device allocations; both times are printed
         BfvCircuit circ(dev);
         zkfhe_prover* pr = nullptr;
         uint8_t seed[32];
-        {
-            std::ifstream ur("/dev/urandom", std::ios::binary);   // the reference seeds its RNG from OS entropy too
-            ur.read((char*)seed, 32);
-        }
-        dev.check(zkfhe_prove_begin(dev.raw(), pk, seed, 0, &pr));
+        os_random(seed, 32);                                       // the reference seeds its RNG from OS entropy too
+        dev.check(zkfhe_prove_begin(dev.raw(), pk, seed, transcript, &pr));
         uint8_t* proof = nullptr;
         size_t len = 0;
         for (int pass = 0; pass < 2; pass++) {
             if (proof) { zkfhe_proof_free(proof); proof = nullptr; }
             circ.builder().reset();
+            os_random(seed, 32);
             dev.check(zkfhe_prove_reset(pr, seed));
             auto t0 = std::chrono::steady_clock::now();
             circ.phase0(in);
@@ -204,7 +291,7 @@ int main(int argc, char** argv) {
         // .snark = "ZKFHESN1" | u32 instances | u32 transcript kind | instances (canonical 32-byte LE) | proof
         uint32_t info[16];
         dev.check(zkfhe_pk_info(pk, info));
-        const uint32_t n_inst = info[12], kind = 0;
+        const uint32_t n_inst = info[12], kind = (uint32_t)transcript;
         std::vector<host::Fr> inst(n_inst);
         if (n_inst) dev.check(zkfhe_witness_download(circ.builder().raw(), 4, (uint8_t*)inst.data()));
         for (auto& v : inst) v = host::from_mont(v);

@@ -262,6 +262,7 @@ public:
         PolyChip pk1_u = half("pk1", "pk1_u", "quotient_1", "quotient_1_times_cyclo", "remainder_1");
         PolyChip c1 = pk1_u.add(P_["e1"]).reduce_by_modulo(Q);                                                // :292-296
         c1.constrain_equality(P_["expected_c1"]);                                                             // :300
+        dev_.status();     // data-dependent asserts recorded by the phase-1 kernels (one synchronisation)
     }
 
 private:

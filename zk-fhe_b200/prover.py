@@ -4,6 +4,7 @@ the schema of the reference's configs/bfv.json.
 """
 import ctypes
 import json
+import os
 
 import numpy as np
 
@@ -45,6 +46,14 @@ class ProvingKey:
         self.ctx._check(self.ctx.lib.zkfhe_vk_export(self.h, _addr(buf), need.value, None))
         return bytes(buf)
 
+    def export_bytes(self):
+        """The proving key as bytes (the reference's data/<name>.pk); `import_key` reads it back."""
+        need = ctypes.c_size_t()
+        self.ctx._check(self.ctx.lib.zkfhe_pk_export(self.h, None, 0, ctypes.byref(need)))
+        buf = bytearray(need.value)
+        self.ctx._check(self.ctx.lib.zkfhe_pk_export(self.h, _addr(buf), need.value, None))
+        return bytes(buf)
+
     def fixed(self, index, form=0):
         """(rows, 4) uint64 Montgomery; form 0 Lagrange, 1 coefficients, 2 extended coset."""
         n = (1 << self.info["k"]) * (4 if form == 2 else 1)
@@ -64,10 +73,15 @@ TRANSCRIPT_BLAKE2B, TRANSCRIPT_POSEIDON = 0, 1
 class Prover:
     """One proof: phase0(witness) -> gamma; (caller runs the phase-1 chip calls); finish(witness) -> bytes."""
 
-    def __init__(self, pk, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B, ctx=None):
-        """`ctx`: the context (stream) this prover runs on; defaults to the key's own context."""
+    def __init__(self, pk, seed=None, transcript=TRANSCRIPT_POSEIDON, ctx=None):
+        """`ctx`: the context (stream) this prover runs on; defaults to the key's own context.
+        `seed`: 32-byte ChaCha20 key of the blinding factors.  None (the default) draws it from the OS, as the
+        reference's `StdRng::from_entropy()` does; a fixed seed gives publicly known blinding factors and is for
+        tests / reproducible benchmarks only."""
         self.pk = pk
         self.ctx = ctx or pk.ctx
+        if seed is None:
+            seed = os.urandom(32)
         assert len(seed) == 32
         self._seed = bytearray(seed)
         h = ctypes.c_void_p()
@@ -112,8 +126,8 @@ class Prover:
         return proof
 
 
-def prove(pk, circuit_factory, inp, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE2B):
-    """The reference's `prove` subcommand for one input: returns (proof bytes, circuit)."""
+def prove(pk, circuit_factory, inp, seed=None, transcript=TRANSCRIPT_POSEIDON):
+    """The reference's `prove` subcommand for one input: returns (proof bytes, circuit).  seed=None: OS entropy."""
     circ = circuit_factory()
     circ.phase0(inp)
     pr = Prover(pk, seed, transcript)
@@ -122,7 +136,7 @@ def prove(pk, circuit_factory, inp, seed=b"\0" * 32, transcript=TRANSCRIPT_BLAKE
     return pr.finish(circ.wit), circ
 
 
-def verify(ctx, vk_bytes, instances, proof, s_g2, transcript=TRANSCRIPT_BLAKE2B):
+def verify(ctx, vk_bytes, instances, proof, s_g2, transcript=TRANSCRIPT_POSEIDON):
     """The reference's `verify` subcommand: True / False.  `instances`: canonical ints; `s_g2`: [tau]_2
     (Context.srs_g2 for the test SRS).  ctx.last_rejection holds the reason of a rejection."""
     inst = b"".join(int(v).to_bytes(32, "little") for v in instances)
@@ -131,6 +145,13 @@ def verify(ctx, vk_bytes, instances, proof, s_g2, transcript=TRANSCRIPT_BLAKE2B)
                                     _addr(proof), len(proof), _addr(s_g2), transcript, ctypes.byref(ok)))
     ctx.last_rejection = None if ok.value else ctx.lib.zkfhe_last_error(ctx.h).decode()
     return bool(ok.value)
+
+
+def import_key(ctx, blob):
+    """A proving key from the bytes `ProvingKey.export_bytes` wrote; the SRS for its k must be loaded on `ctx`."""
+    h = ctypes.c_void_p()
+    ctx._check(ctx.lib.zkfhe_pk_import(ctx.h, _addr(blob), len(blob), ctypes.byref(h)))
+    return ProvingKey(ctx, h)
 
 
 def keygen(witness, k, unusable_rows=109):
