@@ -513,3 +513,308 @@ EXPORT int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ================================================================================================================
+ * Stage (1b): the per-cell witness values of the BFV circuit, on the CPU.
+ *
+ * Restates, in witness-generation mode (values only: no selectors / copy constraints -- what the reference's `prove`
+ * runs once `configs/bfv.json` holds the break points), the calls of
+ *   /root/reference/examples/bfv.rs:70-165 (phase 0) and :172-301 (the phase-1 callback) over
+ *   /root/reference/src/poly_chip.rs (every method) and
+ *   halo2-base v0.3.0-ce GateChip / RangeChip, axiom-eth RlcChip [UPSTREAM-RECALL; the Python
+ *   restatement oracle/halo2_base.py is the line-by-line version this follows and is tested against].
+ * Single-threaded, like the reference's own code (no rayon in the repo).  Cell values that are small
+ * integers are carried as unsigned __int128 and converted to Montgomery form when assigned; the few genuinely
+ * field-valued cells (negated powers of two, chi-key factors, RLC accumulators, is_zero inverses) use Fr arithmetic.
+ * is_zero inverses are batch-inverted at the end, as halo2's `Assigned::Rational` cells are.
+ * ================================================================================================================ */
+typedef struct {
+    fe* a;      size_t n, cap;        /* advice cells (Montgomery) */
+    fe* lk;     size_t nl, lcap;      /* cells_to_lookup values, shared by the contexts, creation order */
+    size_t* inv_at; size_t n_inv, inv_cap;   /* advice cells that hold x and must become 1/x */
+    int overflow;
+} wctx;
+
+static inline void fe_from_u128(fe* r, u128 v) {
+    fe c = {{(uint64_t)v, (uint64_t)(v >> 64), 0, 0}};
+    f_to_mont(&FR, r, &c);
+}
+static inline void w_push(wctx* c, const fe* v) {
+    if (c->n >= c->cap) { c->overflow = 1; return; }
+    c->a[c->n++] = *v;
+}
+static inline void w_push_u(wctx* c, u128 v) { fe t; fe_from_u128(&t, v); w_push(c, &t); }
+static inline void w_look(wctx* c, const fe* v) {
+    if (c->nl >= c->lcap) { c->overflow = 1; return; }
+    c->lk[c->nl++] = *v;
+}
+static inline void w_look_u(wctx* c, u128 v) { fe t; fe_from_u128(&t, v); w_look(c, &t); }
+static const fe FE_ZERO = {{0, 0, 0, 0}};
+
+/* GateChip (values) */
+static void g_add_u(wctx* c, u128 a, u128 b) { w_push_u(c, a); w_push_u(c, b); w_push(c, &FR_ONE); w_push_u(c, a + b); }
+static void g_mul_u(wctx* c, u128 a, u128 b) { w_push(c, &FE_ZERO); w_push_u(c, a); w_push_u(c, b); w_push_u(c, a * b); }
+/* sub on field values: cells [out, b, 1, a] */
+static void g_sub_f(wctx* c, const fe* a, const fe* b, fe* out) {
+    f_sub(&FR, out, a, b);
+    w_push(c, out); w_push(c, b); w_push(c, &FR_ONE); w_push(c, a);
+}
+static void g_mul_f(wctx* c, const fe* a, const fe* b, fe* out) {
+    f_mul(&FR, out, a, b);
+    w_push(c, &FE_ZERO); w_push(c, a); w_push(c, b); w_push(c, out);
+}
+/* is_zero: [is_zero, a, inv, 1, 0, a, is_zero, 0]; returns is_zero as 0 / 1 */
+static int g_is_zero_f(wctx* c, const fe* a) {
+    const int z = fe_is_zero(a);
+    const fe* zf = z ? &FR_ONE : &FE_ZERO;
+    w_push(c, zf); w_push(c, a);
+    if (z) w_push(c, &FR_ONE);                     /* Assigned::Trivial(F::one()) */
+    else {
+        if (c->n_inv < c->inv_cap) c->inv_at[c->n_inv++] = c->n; else c->overflow = 1;
+        w_push(c, a);                              /* placeholder: batch-inverted by w_finish */
+    }
+    w_push(c, &FR_ONE); w_push(c, &FE_ZERO); w_push(c, a); w_push(c, zf); w_push(c, &FE_ZERO);
+    return z;
+}
+static void w_finish(wctx* c) {                    /* Montgomery's trick over the recorded cells */
+    const size_t m = c->n_inv;
+    if (!m) return;
+    fe* pre = (fe*)malloc(sizeof(fe) * m);
+    fe run = FR_ONE;
+    for (size_t i = 0; i < m; i++) { pre[i] = run; f_mul(&FR, &run, &run, &c->a[c->inv_at[i]]); }
+    fe inv;
+    f_inv(&FR, &inv, &run);
+    for (size_t i = m; i-- > 0;) {
+        fe x = c->a[c->inv_at[i]], t;
+        f_mul(&FR, &t, &inv, &pre[i]);
+        c->a[c->inv_at[i]] = t;
+        f_mul(&FR, &inv, &inv, &x);
+    }
+    free(pre);
+    c->n_inv = 0;
+}
+
+/* RangeChip */
+static uint32_t bitlen128(u128 v) { uint32_t b = 0; while (v) { b++; v >>= 1; } return b; }
+static void r_range_check(wctx* c, u128 a, uint32_t range_bits, uint32_t lb) {
+    const uint32_t k = (range_bits + lb - 1) / lb, rem = range_bits % lb;
+    const u128 mask = ((u128)1 << lb) - 1;
+    u128 last;
+    if (k == 1) { w_look_u(c, a); last = a; }
+    else {
+        u128 acc = a & mask;
+        w_push_u(c, acc); w_look_u(c, acc);
+        last = acc;
+        for (uint32_t i = 1; i < k; i++) {
+            const u128 limb = (a >> (lb * i)) & mask;
+            acc += limb << (lb * i);
+            w_push_u(c, limb); w_push_u(c, (u128)1 << (lb * i)); w_push_u(c, acc);
+            w_look_u(c, limb);
+            last = limb;
+        }
+    }
+    if (rem == 1) { w_push(c, &FE_ZERO); w_push_u(c, last); w_push_u(c, last); w_push_u(c, last); }
+    else if (rem > 1) {
+        const u128 m = (u128)1 << (lb - rem);
+        g_mul_u(c, last, m);
+        w_look_u(c, last * m);
+    }
+}
+static void neg_pow2(fe* out, uint32_t bits) { fe p; fe_from_u128(&p, (u128)1 << bits); f_neg(&FR, out, &p); }
+/* cells [a + 2^bits - b, b, 1, a + 2^bits, -2^bits, 1, a], then range_check(first, bits) */
+static void r_check_less_than(wctx* c, u128 a, u128 b, uint32_t bits, uint32_t lb) {
+    const u128 shift_a = ((u128)1 << bits) + a;
+    fe np2;
+    neg_pow2(&np2, bits);
+    w_push_u(c, shift_a - b); w_push_u(c, b); w_push(c, &FR_ONE); w_push_u(c, shift_a); w_push(c, &np2); w_push(c, &FR_ONE); w_push_u(c, a);
+    r_range_check(c, shift_a - b, bits, lb);
+}
+static void r_check_less_than_safe(wctx* c, u128 a, u128 b, uint32_t lb) {
+    const uint32_t rb = (bitlen128(b) + lb - 1) / lb * lb;
+    r_range_check(c, a, rb, lb);
+    r_check_less_than(c, a, b, rb, lb);
+}
+static int r_is_less_than(wctx* c, u128 a, u128 b, uint32_t num_bits, uint32_t lb) {
+    const uint32_t k = (num_bits + lb - 1) / lb, padded = k * lb;
+    const u128 shift_a = ((u128)1 << padded) + a, shifted = shift_a - b;
+    fe np2;
+    neg_pow2(&np2, padded);
+    w_push_u(c, shifted); w_push_u(c, b); w_push(c, &FR_ONE); w_push_u(c, shift_a); w_push(c, &np2); w_push(c, &FR_ONE); w_push_u(c, a);
+    r_range_check(c, shifted, padded + lb, lb);
+    fe top;
+    fe_from_u128(&top, (shifted >> padded) & (((u128)1 << lb) - 1));    /* = cells_to_lookup.last() */
+    return g_is_zero_f(c, &top);
+}
+static u128 r_div_mod(wctx* c, u128 a, uint64_t b, uint32_t a_num_bits, uint32_t lb) {
+    const u128 div = a / b, rem = a % b;
+    w_push_u(c, rem); w_push_u(c, b); w_push_u(c, div); w_push_u(c, a);
+    r_check_less_than_safe(c, div, (((u128)1 << a_num_bits) / b) + 1, lb);
+    r_check_less_than_safe(c, rem, b, lb);
+    return rem;
+}
+/* RlcChip::compute_rlc_fixed_len: cells [in0, in1, acc1, in2, acc2, ...]; returns the final accumulator */
+static void rlc_fixed_len(wctx* c, const u128* in, uint32_t len, const fe* gamma, fe* out) {
+    fe run, x;
+    fe_from_u128(&run, in[0]);
+    w_push(c, &run);
+    for (uint32_t i = 1; i < len; i++) {
+        fe_from_u128(&x, in[i]);
+        f_mul(&FR, &run, &run, gamma);
+        f_add(&FR, &run, &run, &x);
+        w_push(c, &x); w_push(c, &run);
+    }
+    *out = run;
+}
+
+/* PolyChip methods (poly_chip.rs), values only */
+static void pc_constrain_mul(wctx* gate, wctx* rlc, const u128* a, uint32_t la, const u128* b, uint32_t lb_, const u128* cc, uint32_t lc, const fe* gamma) {
+    fe ea, eb, ec;                                                            /* poly_chip.rs:97-104 */
+    rlc_fixed_len(rlc, a, la, gamma, &ea);
+    rlc_fixed_len(rlc, b, lb_, gamma, &eb);
+    rlc_fixed_len(rlc, cc, lc, gamma, &ec);
+    w_push(gate, &FE_ZERO); w_push(gate, &ea); w_push(gate, &eb); w_push(gate, &ec);   /* :107-115 */
+}
+static void pc_in_range(wctx* c, const u128* coeff, uint32_t len, uint64_t z, uint64_t y, uint32_t lb) {   /* :270-317 */
+    const uint32_t ybits = bitlen128(y);
+    for (uint32_t i = 0; i < len; i++) {
+        r_check_less_than_safe(c, coeff[i], y, lb);
+        const int in1 = r_is_less_than(c, coeff[i], (u128)z + 1, ybits, lb);
+        const int not_in2 = r_is_less_than(c, coeff[i], (u128)y - z, ybits, lb);
+        const int in2 = 1 - not_in2;                                         /* not = sub(1, a): [out, a, 1, 1] */
+        w_push_u(c, in2); w_push_u(c, not_in2); w_push(c, &FR_ONE); w_push(c, &FR_ONE);
+        const int nb = 1 - in2, out = in1 | in2;                             /* or: [1-b, 1, b, 1, b, a, 1-b, out] */
+        w_push_u(c, nb); w_push(c, &FR_ONE); w_push_u(c, in2); w_push(c, &FR_ONE); w_push_u(c, in2); w_push_u(c, in1); w_push_u(c, nb); w_push_u(c, out);
+    }
+}
+static void pc_chi_key(wctx* c, const u128* coeff, uint32_t len, uint64_t z) {                          /* :320-354 */
+    fe zf, one = FR_ONE, zero = FE_ZERO;
+    fe_from_u128(&zf, z);
+    for (uint32_t i = 0; i < len; i++) {
+        fe v, f1, f2, f3, f12, f123;
+        fe_from_u128(&v, coeff[i]);
+        g_sub_f(c, &v, &zero, &f1);
+        g_sub_f(c, &v, &one, &f2);
+        g_sub_f(c, &v, &zf, &f3);
+        g_mul_f(c, &f1, &f2, &f12);
+        g_mul_f(c, &f12, &f3, &f123);
+    }
+}
+static void pc_in_modulus_field(wctx* c, const u128* coeff, uint32_t len, uint64_t q, uint32_t lb) {    /* :357-366 */
+    for (uint32_t i = 0; i < len; i++) r_check_less_than_safe(c, coeff[i], q, lb);
+}
+static void pc_reduce_by_modulo(wctx* c, const u128* coeff, uint32_t len, uint64_t q, uint32_t nbits, uint32_t lb, u128* out) {   /* :226-252 */
+    for (uint32_t i = 0; i < len; i++) out[i] = r_div_mod(c, coeff[i], q, nbits, lb);
+}
+static void pc_add(wctx* c, const u128* a, const u128* b, uint32_t len, u128* out) {                    /* :122-144 */
+    for (uint32_t i = 0; i < len; i++) { g_add_u(c, a[i], b[i]); out[i] = a[i] + b[i]; }
+}
+static void pc_constrain_equality(wctx* c, const u128* a, const u128* b, uint32_t len) {                /* :255-264 */
+    for (uint32_t i = 0; i < len; i++) {
+        fe x, y, d;
+        fe_from_u128(&x, a[i]); fe_from_u128(&y, b[i]);
+        g_sub_f(c, &x, &y, &d);
+        g_is_zero_f(c, &d);
+    }
+}
+
+static uint32_t log2_ceil_u64(uint64_t x) { uint32_t b = bitlen128(x); return b - ((x & (x - 1)) == 0 ? 1 : 0); }
+
+/* in[9]: pk0, pk1, m, u, e0, e1, c0, c1 (N values each), cyclo (N + 1), big-endian, already parsed to u64.
+ * adv0 / adv1 / adv2: flat advice of the phase-0 gate, phase-1 gate and phase-1 RLC contexts; lk: lookup cells.
+ * counts_out = {cells0, cells1, cells2, lookups}.  Returns 0, -1 where the reference asserts / panics, -2 when a
+ * capacity is too small. */
+EXPORT int orc_bfv_witness(const uint64_t* const* in, uint32_t N, uint64_t Q, uint64_t T, uint64_t B, uint32_t lookup_bits,
+                           const uint64_t* gamma_mont, uint64_t* adv0, uint64_t cap0, uint64_t* adv1, uint64_t cap1,
+                           uint64_t* adv2, uint64_t cap2, uint64_t* lk, uint64_t capl, uint64_t* counts_out) {
+    const uint32_t lb = lookup_bits, L2 = 2 * N - 1, LC = N + 1, LR = 2 * N + 1;
+    const uint32_t qbits = bitlen128(Q);
+    for (int p = 0; p < 9; p++)
+        for (uint32_t i = 0; i < (p == 8 ? LC : N); i++) if (in[p][i] > Q) return -1;                  /* poly.rs:28 */
+    size_t* inv_at = (size_t*)malloc(sizeof(size_t) * (size_t)(8 * N + 64));
+    wctx c0 = {(fe*)adv0, 0, cap0, (fe*)lk, 0, capl, inv_at, 0, 0, 0};
+    /* ---- phase 0 (bfv.rs:70-165) ---- */
+    u128 *P[9];
+    for (int p = 0; p < 9; p++) {
+        const uint32_t len = p == 8 ? LC : N;
+        P[p] = (u128*)malloc(sizeof(u128) * len);
+        for (uint32_t i = 0; i < len; i++) P[p][i] = in[p][i];
+    }
+    enum { PK0, PK1, M, U, E0, E1, C0, C1, CY };
+    for (int p = 0; p < 9; p++) for (uint32_t i = 0; i < (p == 8 ? LC : N); i++) w_push_u(&c0, P[p][i]);   /* :101-109 */
+    w_push_u(&c0, Q / T);                                                                                 /* :115 */
+    u128 *pku[2], *quo[2], *qtc[2], *rem[2];
+    uint64_t* tmp_lohi = (uint64_t*)malloc(sizeof(uint64_t) * 2 * (size_t)LR);
+    uint64_t* red = (uint64_t*)malloc(sizeof(uint64_t) * L2);
+    uint64_t* q64 = (uint64_t*)malloc(sizeof(uint64_t) * LC);
+    uint64_t* r64 = (uint64_t*)malloc(sizeof(uint64_t) * LR);
+    int rc = 0;
+    for (int h = 0; h < 2; h++) {
+        pku[h] = (u128*)malloc(sizeof(u128) * L2);
+        quo[h] = (u128*)malloc(sizeof(u128) * LC);
+        qtc[h] = (u128*)malloc(sizeof(u128) * LR);
+        rem[h] = (u128*)malloc(sizeof(u128) * LR);
+        orc_poly_mul(in[h == 0 ? PK0 : PK1], in[U], N, tmp_lohi);                                         /* :131-132 */
+        for (uint32_t i = 0; i < L2; i++) pku[h][i] = ((u128)tmp_lohi[2 * i + 1] << 64) | tmp_lohi[2 * i];
+        orc_poly_reduce(tmp_lohi, L2, Q, red);                                                            /* :139-140 */
+        if (orc_divide_by_cyclo(red, L2, in[CY], LC, Q, q64, r64) != 0) rc = -1;                          /* :143-146 */
+        orc_poly_mul(q64, in[CY], LC, tmp_lohi);                                                          /* :149-150 */
+        for (uint32_t i = 0; i < LC; i++) quo[h][i] = q64[i];
+        for (uint32_t i = 0; i < LR; i++) { qtc[h][i] = ((u128)tmp_lohi[2 * i + 1] << 64) | tmp_lohi[2 * i]; rem[h][i] = r64[i]; }
+    }
+    for (int h = 0; h < 2; h++) for (uint32_t i = 0; i < L2; i++) w_push_u(&c0, pku[h][i]);               /* :135-136 */
+    for (int h = 0; h < 2; h++) for (uint32_t i = 0; i < LC; i++) w_push_u(&c0, quo[h][i]);               /* :156-157 */
+    for (int h = 0; h < 2; h++) for (uint32_t i = 0; i < LR; i++) w_push_u(&c0, qtc[h][i]);               /* :160-161 */
+    for (int h = 0; h < 2; h++) for (uint32_t i = 0; i < LR; i++) w_push_u(&c0, rem[h][i]);               /* :164-165 */
+    /* ---- phase 1 (bfv.rs:172-301) ---- */
+    wctx g = {(fe*)adv1, 0, cap1, (fe*)lk, c0.nl, capl, inv_at, 0, (size_t)(8 * N + 64), 0};
+    wctx r = {(fe*)adv2, 0, cap2, (fe*)lk, 0, 0, NULL, 0, 0, 0};
+    const fe* gamma = (const fe*)gamma_mont;
+    pc_in_range(&g, P[E0], N, B, Q, lb);                                                                  /* :189 */
+    pc_in_range(&g, P[E1], N, B, Q, lb);                                                                  /* :190 */
+    pc_chi_key(&g, P[U], N, Q - 1);                                                                       /* :201 */
+    pc_in_range(&g, P[M], N, T / 2, Q, lb);                                                               /* :210 */
+    u128* s = (u128*)malloc(sizeof(u128) * LR);
+    u128* s_mod = (u128*)malloc(sizeof(u128) * LR);
+    u128* red_pk = (u128*)malloc(sizeof(u128) * L2);
+    u128* cres = (u128*)malloc(sizeof(u128) * N);
+    u128* t1 = (u128*)malloc(sizeof(u128) * N);
+    const uint32_t pku_bits = qbits + qbits + log2_ceil_u64(N);                  /* poly.rs:101 on pk * u */
+    const uint32_t qtc_bits = qbits + qbits + log2_ceil_u64((uint64_t)N + 1);    /* poly.rs:101 on quotient * cyclo */
+    for (int h = 0; h < 2; h++) {
+        pc_constrain_mul(&g, &r, P[h == 0 ? PK0 : PK1], N, P[U], N, pku[h], L2, gamma);                   /* :215 / :264 */
+        pc_reduce_by_modulo(&g, pku[h], L2, Q, pku_bits, lb, red_pk);                                     /* :219 / :268 */
+        pc_in_modulus_field(&g, quo[h], LC, Q, lb);                                                       /* :225 / :274 */
+        pc_in_modulus_field(&g, rem[h], LR, Q, lb);                                                       /* :226 / :275 */
+        /* reduce_by_cyclo (poly_chip.rs:183-223) */
+        pc_constrain_mul(&g, &r, quo[h], LC, P[CY], LC, qtc[h], LR, gamma);                               /* :205 */
+        pc_add(&g, qtc[h], rem[h], LR, s);                                                                /* :208 */
+        const uint32_t s_bits = (qtc_bits > qbits ? qtc_bits : qbits) + 1;
+        pc_reduce_by_modulo(&g, s, LR, Q, s_bits, lb, s_mod);                                             /* :211 */
+        pc_constrain_equality(&g, s_mod + (LR - L2), red_pk, L2);                                         /* :214-217 */
+        const u128* pk_u_red = rem[h] + (LR - N);                                                         /* :222 */
+        if (h == 0) {
+            const uint64_t delta = Q / T;
+            for (uint32_t i = 0; i < N; i++) { g_mul_u(&g, P[M][i], delta); t1[i] = P[M][i] * delta; }    /* :243 */
+            pc_add(&g, pk_u_red, t1, N, cres);                                                            /* :247 */
+            pc_add(&g, cres, P[E0], N, t1);                                                               /* :251 */
+            const uint32_t mb = qbits + bitlen128(delta), cb = (qbits > mb ? qbits : mb) + 1;
+            pc_reduce_by_modulo(&g, t1, N, Q, (cb > qbits ? cb : qbits) + 1, lb, cres);                   /* :255 */
+            pc_constrain_equality(&g, cres, P[C0], N);                                                    /* :259 */
+        } else {
+            pc_add(&g, pk_u_red, P[E1], N, t1);                                                           /* :292 */
+            pc_reduce_by_modulo(&g, t1, N, Q, qbits + 1, lb, cres);                                       /* :296 */
+            pc_constrain_equality(&g, cres, P[C1], N);                                                    /* :300 */
+        }
+    }
+    w_finish(&g);
+    counts_out[0] = c0.n; counts_out[1] = g.n; counts_out[2] = r.n; counts_out[3] = g.nl;
+    if (c0.overflow || g.overflow || r.overflow) rc = -2;
+    for (int p = 0; p < 9; p++) free(P[p]);
+    for (int h = 0; h < 2; h++) { free(pku[h]); free(quo[h]); free(qtc[h]); free(rem[h]); }
+    free(tmp_lohi); free(red); free(q64); free(r64); free(s); free(s_mod); free(red_pk); free(cres); free(t1); free(inv_at);
+    return rc;
+}
+
+EXPORT void orc_from_mont_array(int which, const uint64_t* in, uint64_t* out, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) f_from_mont(which ? &FQ : &FR, (fe*)(out + 4 * i), (const fe*)(in + 4 * i));
+}

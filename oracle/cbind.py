@@ -38,6 +38,9 @@ def lib():
         L.orc_divide_by_cyclo.argtypes = [vp, u32, vp, u32, u64, vp, vp]
         L.orc_divide_by_cyclo.restype = ci
         L.orc_num_threads.restype = ci
+        L.orc_from_mont_array.argtypes = [ci, vp, vp, u64]
+        L.orc_bfv_witness.argtypes = [vp, u32, u64, u64, u64, u32, vp, vp, u64, vp, u64, vp, u64, vp, u64, vp]
+        L.orc_bfv_witness.restype = ci
         _lib = L
     return _lib
 
@@ -121,3 +124,31 @@ def divide_by_cyclo(dividend, cyclo, q):
         from .poly import OracleError
         raise OracleError("divide_by_cyclo: reference panics on this input")
     return [int(x) for x in quo], [int(x) for x in rem]
+
+
+def bfv_witness(inp, N, Q, T, B, gamma, lookup_bits=8, caps=None):
+    """Stage (1) on the CPU in C (orc_bfv_witness): `inp` is a bfv.in dict (decimal strings or ints).  Returns
+    (adv0, adv1, adv2, lookups) as (cells, 4) uint64 Montgomery arrays -- the flat advice of the phase-0 gate,
+    phase-1 gate and phase-1 RLC contexts and the cells_to_lookup values, in creation order."""
+    from .bfv import INPUT_KEYS
+    from .poly import OracleError
+    arrs = [np.array([int(x) for x in inp[k]], dtype=np.uint64) for k in INPUT_KEYS]
+    ptrs = (ctypes.c_void_p * 9)(*[a.ctypes.data for a in arrs])
+    if caps is None:       # generous bounds from the cell-cost model (SURVEY App. B): <= 1300 cells per input coefficient
+        caps = (32 * N, 1300 * N, 40 * N, 320 * N)
+    bufs = [np.zeros((c, 4), np.uint64) for c in caps]
+    g = ints_to_u64x4([gamma * (1 << 256) % int("30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001", 16)])
+    counts = np.zeros(4, np.uint64)
+    rc = lib().orc_bfv_witness(ctypes.addressof(ptrs), N, Q, T, B, lookup_bits, _p(g), _p(bufs[0]), caps[0], _p(bufs[1]), caps[1],
+                               _p(bufs[2]), caps[2], _p(bufs[3]), caps[3], _p(counts))
+    if rc == -1:
+        raise OracleError("stage (1): the reference asserts / panics on this input")
+    if rc != 0:
+        raise RuntimeError(f"orc_bfv_witness: buffer too small or inconsistent witness (rc={rc})")
+    return tuple(b[:int(c)] for b, c in zip(bufs, counts))
+
+
+def from_mont_array(arr, which=0):
+    out = np.empty_like(arr)
+    lib().orc_from_mont_array(which, _p(arr), _p(out), arr.shape[0])
+    return out

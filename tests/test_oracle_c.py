@@ -85,3 +85,74 @@ def test_c_stage1_matches_poly_rs_restatement(bfv_input):
     assert q == q_py.coefficients and r == r_py.coefficients
     z = cbind.divide_by_cyclo([0] * 2047, [0] * 1025, Q)
     assert z == ([0] * 1025, [0] * 2049)
+
+
+# ---- stage (1) in C (orc_bfv_witness): the CPU arm's witness generator ---------------------------------------
+def _canon(arr):
+    return cbind.u64x4_to_ints(cbind.from_mont_array(np.ascontiguousarray(arr)))
+
+
+def test_c_witness_equals_python_oracle_on_bfv_in(bfv_input, golden_gamma, oracle_tables, digests):
+    """All 1,288,314 advice cells and 286,756 lookup cells of bfv.in, cell by cell, against oracle/bfv.py (itself
+    pinned by c0 / c1 of bfv.in and by configs/bfv.json) and against the committed digests."""
+    import hashlib
+    a0, a1, a2, lk = cbind.bfv_witness(bfv_input, 1024, 536870909, 7, 19, golden_gamma)
+    tab = oracle_tables
+    assert _canon(a0) == tab["phase0"].ctx.advice
+    assert _canon(a1) == tab["ctx_gate"].advice
+    assert _canon(a2) == tab["ctx_rlc"].advice
+    assert _canon(lk) == [v for col in tab["lookup"] for v in col]
+    for key, arr in (("phase0_advice_sha256", a0), ("phase1_gate_advice_sha256", a1), ("phase1_rlc_advice_sha256", a2),
+                     ("lookup_cells_sha256", lk)):
+        assert hashlib.sha256(cbind.from_mont_array(np.ascontiguousarray(arr)).tobytes()).hexdigest() == digests[key]
+
+
+def test_c_witness_keygen_input_and_small_parameters(bfv_empty_input):
+    """The all-zero keygen input (zero shortcut of divide_by_cyclo, src/poly.rs:118-123) and a small (N, Q) against
+    the Python oracle; a coefficient above Q is the reference's assert at src/poly.rs:28."""
+    import pytest
+    from oracle import bfv as obfv
+    from oracle.poly import OracleError
+    a0, a1, a2, lk = cbind.bfv_witness(bfv_empty_input, 1024, 536870909, 7, 19, 7)
+    assert (a0.shape[0], a1.shape[0], a2.shape[0], lk.shape[0]) == (23558, 1231992, 32764, 286756)
+    rng = random.Random(4)
+    N, Q, T, B = 16, 65521, 5, 9
+    par = obfv.BfvParams(N=N, Q=Q, T=T, B=B)
+    pk0, pk1 = [rng.randrange(Q) for _ in range(N)], [rng.randrange(Q) for _ in range(N)]
+    u = [rng.choice([0, 1, Q - 1]) for _ in range(N)]
+    e0, e1 = [rng.randrange(-B, B + 1) % Q for _ in range(N)], [rng.randrange(-B, B + 1) % Q for _ in range(N)]
+    m = [rng.randrange(-(T // 2), T // 2 + 1) % Q for _ in range(N)]
+
+    def ring_mul(a, b):
+        p = [0] * (2 * N - 1)
+        for i in range(N):
+            for j in range(N):
+                p[i + j] += a[i] * b[j]
+        return [(p[N - 1 + i] - (p[i - 1] if i else 0)) % Q for i in range(N)]
+
+    c0 = [(x + (Q // T) * mm + e) % Q for x, mm, e in zip(ring_mul(pk0, u), m, e0)]
+    c1 = [(x + e) % Q for x, e in zip(ring_mul(pk1, u), e1)]
+    inp = {"pk0": pk0, "pk1": pk1, "m": m, "u": u, "e0": e0, "e1": e1, "c0": c0, "c1": c1, "cyclo": [1] + [0] * (N - 1) + [1]}
+    sinp = {k: [str(x) for x in v] for k, v in inp.items()}
+    tab = obfv.build_tables(sinp, 12345, par, k=9, unusable_rows=20)
+    a0, a1, a2, lk = cbind.bfv_witness(inp, N, Q, T, B, 12345)
+    assert _canon(a0) == tab["phase0"].ctx.advice
+    assert _canon(a1) == tab["ctx_gate"].advice
+    assert _canon(a2) == tab["ctx_rlc"].advice
+    assert _canon(lk) == [v for col in tab["lookup"] for v in col]
+    bad = dict(inp)
+    bad["e0"] = [Q + 1] + e0[1:]
+    with pytest.raises(OracleError):
+        cbind.bfv_witness(bad, N, Q, T, B, 12345)
+
+
+def test_bench_cpu_arm_inputs_are_valid_encryptions():
+    """bench.py's CPU-arm input generator: c0, c1 satisfy the circuit's equalities (no is_equal cell is 0)."""
+    import bench
+    inp = bench.cpu_synth_input(np.random.default_rng(3))
+    N, Q = 1024, 536870909
+    a0, a1, a2, lk = cbind.bfv_witness(inp, N, Q, 7, 19, 99)
+    # the last call is c1.constrain_equality (12 cells per coefficient, is_zero flag at cell 4 of each block)
+    tail = _canon(a1[-12 * N:])
+    assert all(tail[12 * i + 4] == 1 for i in range(N))
+    assert bench.host_threads() >= 1
