@@ -287,6 +287,25 @@ int zkfhe_prove_reset(zkfhe_prover* pr, const uint8_t* seed32);
 void zkfhe_prover_free(zkfhe_prover* pr);
 void zkfhe_proof_free(uint8_t* proof);
 
+/* ---- one proof over several GPUs (nothing of the kind exists in the reference) ---------
+ * SPMD: every rank holds the same proving key and SRS on its own GPU and makes the SAME sequence of witness / prove
+ * calls on the same input and seed.  Inside zkfhe_prove_* each commitment phase is then sharded by column (rank r
+ * commits the block zkfhe_shard_range gives it; one ncclAllGather of 64 bytes per column) and the quotient by coset
+ * of the extended domain (rank r evaluates the identities on coset r mod 4 -- with more than four ranks the ranks of
+ * a coset split the expression list -- and one ncclAllGather moves n x 32 bytes per rank).  Everything else is
+ * replicated, so every rank returns the same proof, byte-identical to the single-GPU proof.
+ * libnccl.so.2 is loaded with dlopen on first use.  Rank counts 1, 2 and >= 4 are supported (3 does not divide the
+ * four cosets). */
+int zkfhe_comm_unique_id(uint8_t* out128);                 /* ncclGetUniqueId: call on one rank, hand the bytes to all */
+int zkfhe_comm_init(zkfhe_ctx* ctx, int rank, int n_ranks, const uint8_t* id128);   /* collective: ncclCommInitRank */
+int zkfhe_comm_destroy(zkfhe_ctx* ctx);
+int zkfhe_comm_info(const zkfhe_ctx* ctx, int* rank, int* n_ranks, int* virtual_ranks);
+/* Testing on ONE GPU: compute the `n_ranks` shards one after the other on this context, no collective (0 or 1
+ * switches it off).  The proof must not change. */
+int zkfhe_set_virtual_ranks(zkfhe_ctx* ctx, int n_ranks);
+/* The contiguous block [lo, hi) of `count` items that shard `rank` of `n_ranks` owns (ceil(count / n_ranks) each). */
+int zkfhe_shard_range(uint32_t count, uint32_t n_ranks, uint32_t rank, uint32_t* lo, uint32_t* hi);
+
 /* ---- verify (reference `verify` subcommand, README.md:48-54) --------------------------------
  * The pairing check halo2-axiom's VerifierSHPLONK ends with: is prod_i e(P_i, Q_i) == 1 ?
  * P_i are 64-byte G1 affine points (x | y), Q_i 128-byte G2 affine points (x.c0 | x.c1 | y.c0 | y.c1,
@@ -322,6 +341,11 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain);
  * `out` as canonical 32-byte scalars (out = NULL only counts them). */
 int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges);
 
+/* Host arithmetic speed on the calling thread, ns per operation: kind 0 = one Poseidon permutation (the form the
+ * transcript runs), 1 = one dependent Fr product, 2 = one plain-form permutation.  `features` (optional) receives a
+ * short description of the code path (BMI2 / ADX product or the portable one). */
+int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap);
+
 /* ---- timing hook -------------------------------------------------------------------------
  * Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last
  * NTT / MSM call: the butterfly passes for NTT, the bucket-accumulation kernel for MSM. */
@@ -330,7 +354,8 @@ float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx);
  * the context's stream around every launch of that category, so whole-proof shares can be read
  * without a profiler).  category 0: MSM bucket accumulation (units = scalar/point pairs),
  * 1: NTT passes (units = field elements transformed), 2: MSM counting sort, 3: MSM bucket folding,
- * 4: MSM final reduction, 5: no time -- units = point additions issued by the accumulate kernel
+ * 4: MSM final reduction, 7: NCCL collectives of a sharded proof (units = bytes gathered),
+ * 5: no time -- units = point additions issued by the accumulate kernel
  * (non-zero signed digits), the numerator of the IMAD-pipe roofline; 6: no time -- units = field
  * products issued by the NTT passes (butterflies + 4-step twiddles + coset / n^-1 factors). */
 int zkfhe_timing_reset(zkfhe_ctx* ctx);

@@ -304,3 +304,61 @@ def test_small_circuit_end_to_end_both_transcripts(transcript):
     with pytest.raises(verifier.VerifyError):
         verifier.verify(vk, inst, proof, TAU, transcript_kind=1 - transcript)
     ctx.close()
+
+
+# ---- one proof sharded over several (here: virtual) ranks ------------------------------------------------------
+@pytest.mark.parametrize("G", [2, 3, 4, 5, 8])
+def test_sharded_proof_is_byte_identical_small_circuit(G):
+    """Column-sharded commitment phases and the coset-sharded quotient (zkfhe_set_virtual_ranks: all G shards computed
+    on this GPU, no collective) must give the single-GPU proof byte for byte -- every rank count, incl. the ones where a
+    shard takes several cosets (G < 4) or the shards of a coset split the expression list (G > 4)."""
+    import zk_fhe_b200
+    from zk_fhe_b200 import bfv, prover
+    ctx = zk_fhe_b200.Context(0)
+    k, unusable = 10, 20
+    ctx.srs_setup(k, TAU)
+    params = bfv.BfvParams(N=16, Q=536870909, T=7, B=19)
+    zeros = {key: ["0"] * (17 if key == "cyclo" else 16) for key in bfv.INPUT_KEYS}
+    kg = bfv.BfvCircuit(ctx, params, record=True)
+    kg.phase0(zeros).phase1(3)
+    pk = prover.keygen(kg.wit, k, unusable)
+    inp = _synthetic_input(random.Random(45), 16, params.Q, params.T, params.B)
+    want, inst = _prove(ctx, pk, inp, bytes(range(32)), params, 0)
+    ctx.set_virtual_ranks(G)
+    assert ctx.comm_info() == (0, 1, G)
+    got, _ = _prove(ctx, pk, inp, bytes(range(32)), params, 0)
+    assert got == want
+    ctx.set_virtual_ranks(0)
+    again, _ = _prove(ctx, pk, inp, bytes(range(32)), params, 0)
+    assert again == want
+    assert verifier.verify(_vk(pk, unusable), inst, got, TAU)
+    ctx.close()
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_sharded_proof_is_byte_identical_config1(ctx13, pk13, bfv_input, G):
+    want, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    ctx13.set_virtual_ranks(G)
+    try:
+        got, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
+    finally:
+        ctx13.set_virtual_ranks(0)
+    assert got == want
+
+
+def test_sharded_proof_over_nccl_two_gpus(tmp_path):
+    """Two processes, two GPUs, one proof (tools/sharded_prove.py under torchrun): both ranks must return the bytes of
+    the single-GPU proof.  Skipped on a one-GPU box (the virtual-rank tests above cover the arithmetic there)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "sharded.json"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tools", "sharded_prove.py"), "--k", "13", "--proofs", "2", "--out", str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.load(open(out))
+    assert res["identical_to_single_gpu"] is True and res["n_ranks"] == 2

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkfhe_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu", "verifier.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu", "verifier.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -83,7 +83,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}")
         with open(obj + ".stamp", "w") as f:
             f.write(ostamp)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     # the `bfv` example entrypoint (host C++ mirror of examples/bfv.rs over the C ABI)
     bindir = os.path.join(HERE, "bin")

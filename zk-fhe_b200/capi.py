@@ -54,6 +54,13 @@ _SIGNATURES = {
     "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,
                                 _c.POINTER(_c.c_int)]),
     "zkfhe_poseidon_permute": (_c.c_int, [_u8p, _c.c_int]),
+    "zkfhe_comm_unique_id": (_c.c_int, [_u8p]),
+    "zkfhe_comm_init": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _u8p]),
+    "zkfhe_comm_destroy": (_c.c_int, [_c.c_void_p]),
+    "zkfhe_comm_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
+    "zkfhe_set_virtual_ranks": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "zkfhe_shard_range": (_c.c_int, [_c.c_uint32, _c.c_uint32, _c.c_uint32, _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32)]),
+    "zkfhe_host_microbench": (_c.c_int, [_c.c_int, _c.c_uint32, _c.POINTER(_c.c_double), _c.c_char_p, _c.c_size_t]),
     "zkfhe_transcript_replay": (_c.c_int, [_c.c_int, _u8p, _c.c_size_t, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_pk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_pk_import": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_void_p)]),
@@ -184,6 +191,24 @@ def _addr(buf):
     raise TypeError(type(buf))
 
 
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (ncclGetUniqueId); create on one rank, broadcast to the others."""
+    out = bytearray(128)
+    rc = load_library().zkfhe_comm_unique_id(_addr(out))
+    if rc != OK:
+        raise ZkfheError(rc, "zkfhe_comm_unique_id failed (is libnccl.so.2 loadable?)")
+    return bytes(out)
+
+
+def shard_range(count, n_ranks, rank):
+    """[lo, hi): the block of `count` items shard `rank` of `n_ranks` owns."""
+    lo, hi = ctypes.c_uint32(), ctypes.c_uint32()
+    rc = load_library().zkfhe_shard_range(count, n_ranks, rank, ctypes.byref(lo), ctypes.byref(hi))
+    if rc != OK:
+        raise ZkfheError(rc, "zkfhe_shard_range: bad arguments")
+    return lo.value, hi.value
+
+
 class Context:
     """One GPU, one stream.  Mirrors the zkfhe_ctx lifetime."""
 
@@ -249,6 +274,25 @@ class Context:
         ms, ops = ctypes.c_float(), ctypes.c_uint64()
         self._check(self.lib.zkfhe_microbench(self.h, kind, iters, ctypes.byref(ms), ctypes.byref(ops)))
         return float(ms.value), int(ops.value)
+
+    # -- one proof over several GPUs ---------------------------------------------
+    def comm_init(self, rank, n_ranks, unique_id):
+        """Collective: bind an NCCL communicator to this context (unique_id: 128 bytes from comm_unique_id on one rank)."""
+        assert len(unique_id) == 128
+        self._check(self.lib.zkfhe_comm_init(self.h, rank, n_ranks, _addr(bytes(unique_id))))
+
+    def comm_destroy(self):
+        self._check(self.lib.zkfhe_comm_destroy(self.h))
+
+    def comm_info(self):
+        """(rank, n_ranks, virtual_ranks)"""
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.zkfhe_comm_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_virtual_ranks(self, n_ranks):
+        """Testing on one GPU: compute the shards of an `n_ranks`-way sharded proof one after the other here."""
+        self._check(self.lib.zkfhe_set_virtual_ranks(self.h, n_ranks))
 
     # -- stage (3) ----------------------------------------------------------
     def ntt_fr(self, data, log_n, batch, inverse=False, coset=False):

@@ -1,6 +1,7 @@
 // C ABI of libzkfhe_b200 (include/zkfhe_b200.h): context lifecycle, host<->device
 // staging and the on-device self test.  Compute lives in ntt.cu / msm.cu /
 // witness.cu; nothing here falls back to the CPU.
+#include <chrono>
 #include <new>
 #include <cstring>
 #include "common.cuh"
@@ -179,6 +180,28 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain) {
     return ZKFHE_OK;
 }
 
+// ns per operation on the calling host thread: kind 0 = Poseidon permutation (optimised form), 1 = dependent Fr
+// products, 2 = plain-form permutation.  `features` (optional, >= 64 bytes) says which product the host code runs.
+int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap) {
+    if (!ns_per_op || !iters || kind < 0 || kind > 2) return ZKFHE_ERR_ARG;
+    host::Fr s[POSEIDON_T];
+    for (int i = 0; i < POSEIDON_T; i++) s[i] = host::from_u64(i + 1);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (kind == 0) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute(s);
+    else if (kind == 2) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute_plain(s);
+    else for (uint32_t i = 0; i < iters; i++) s[0] = host::mul(s[0], s[1]);
+    *ns_per_op = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / iters;
+    if (s[0].is_zero() && s[1].is_zero()) *ns_per_op = -1;       // keeps the loop observable
+    if (features && cap) {
+#if defined(__x86_64__) && defined(__GNUC__)
+        snprintf(features, cap, "%s", host::cpu_has_adx() ? "fr_mul: mulx/adcx/adox" : "fr_mul: portable (no BMI2/ADX)");
+#else
+        snprintf(features, cap, "fr_mul: portable");
+#endif
+    }
+    return ZKFHE_OK;
+}
+
 int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges) {
     if (!script || !n_challenges || (kind != host::TRANSCRIPT_BLAKE2B && kind != host::TRANSCRIPT_POSEIDON)) return ZKFHE_ERR_ARG;
     host::Transcript tr(kind);
@@ -236,6 +259,7 @@ void zkfhe_destroy(zkfhe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    zkfhe_comm_destroy(ctx);
     for (auto& kv : ctx->domains) { cudaFree(kv.second.tw_fwd); cudaFree(kv.second.tw_inv); cudaFree(kv.second.tw_inv_s); }
     for (auto& b : ctx->basis) if (b.table && !b.shared) { cudaFree(b.table); if (b.table_s) cudaFree(b.table_s); }
     for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);

@@ -58,10 +58,18 @@ struct zkfhe_ctx {
     std::vector<SpanInfo> ev_info;
     size_t ev_used = 0, call_mark = 0;
     uint64_t ntt_products = 0;                   // butterflies + twiddle / coset / scaling products since timing_reset
+    // one proof sharded over several GPUs (comm.cu): rank / size of the NCCL communicator bound to this context, or
+    // -- for tests on one GPU -- `virtual_ranks` shards computed one after the other by this context
+    void* nccl_comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    int virtual_ranks = 0;
+    float comm_ms = 0;                           // device time spent in collectives since timing_reset (category 7)
+    uint32_t comm_calls = 0;
 };
 enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4,
        ZK_CAT_MSM_REFS = 5 /* no time: units = point additions issued by the accumulate kernel */, 
-       ZK_CAT_NTT_PRODUCTS = 6 /* no time: units = field products issued by the NTT passes */, ZK_CAT_COUNT = 7 };
+       ZK_CAT_NTT_PRODUCTS = 6 /* no time: units = field products issued by the NTT passes */,
+       ZK_CAT_COMM = 7 /* NCCL collectives of a sharded proof (units = bytes gathered) */, ZK_CAT_COUNT = 8 };
 
 namespace zkfhe {
 
@@ -149,5 +157,25 @@ int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d
 int fr_convert(zkfhe_ctx* ctx, fr_t* d, uint64_t count, int to_montgomery);
 int points_to_canonical(zkfhe_ctx* ctx, g1_affine* d_pts, uint32_t count);
 int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mismatches);
+
+// ---- sharding of one proof over ranks (comm.cu) ----------------------------------------------------------------
+// G shards; this process computes shards [first, last): its own rank under NCCL, all of them in virtual mode, the
+// single shard 0 otherwise.
+struct Shards { uint32_t G, first, last; };
+inline Shards shards_of(const zkfhe_ctx* ctx) {
+    if (ctx->nccl_comm) return Shards{(uint32_t)ctx->n_ranks, (uint32_t)ctx->rank, (uint32_t)ctx->rank + 1};
+    if (ctx->virtual_ranks > 1) return Shards{(uint32_t)ctx->virtual_ranks, 0, (uint32_t)ctx->virtual_ranks};
+    return Shards{1, 0, 1};
+}
+// contiguous block of shard v when `count` items are split over G shards: per = ceil(count / G) items per shard
+inline uint32_t shard_per(uint32_t count, uint32_t G) { return (count + G - 1) / G; }
+inline void shard_range(uint32_t count, uint32_t G, uint32_t v, uint32_t* lo, uint32_t* hi) {
+    const uint32_t per = shard_per(count, G);
+    *lo = v * per < count ? v * per : count;
+    *hi = *lo + per < count ? *lo + per : count;
+}
+// in place: every rank has written its block [rank * bytes_per_rank, (rank + 1) * bytes_per_rank) of `d_buf`; afterwards
+// every rank holds all blocks.  No-op without a communicator (virtual shards were written by this process).
+int comm_allgather(zkfhe_ctx* ctx, void* d_buf, size_t bytes_per_rank);
 
 }  // namespace zkfhe

@@ -279,7 +279,11 @@ struct QArgs {
     const fr_t* ypow;        // y^t, t < NE
     const fr_t* delta_pow;
     fr_t* part;              // [groups][4n] partial sums
-    uint32_t n4, rot;        // 4n, extended-index step of one base-domain rotation (= 4)
+    uint32_t n4, rot;        // rows of E handled here (4n: the whole extended coset; n: one coset of H inside it) and the
+                             // row step of one base-domain rotation (4 resp. 1)
+    uint64_t f_stride;       // elements between fixed columns in F (always 4n)
+    uint32_t f_rs, f_ro;     // row r of E is extended-domain index r * f_rs + f_ro (1, 0 resp. 4, coset)
+    uint32_t grp_base, perm_base, lookup_base;   // first gate group / permutation chunk / lookup handled by this launch
     uint32_t n_gate, n_rlc, rlc_base, n_advice, n_lookup, n_chunks, n_perm, NE;
     uint32_t zp_base, zl_base, ap_base, lookup_adv_base, usable;
     uint32_t fx_qgate, fx_qrlc, fx_const, fx_table, fx_l0, fx_sigma;
@@ -287,10 +291,10 @@ struct QArgs {
     fr_t gamma_rlc, beta, gamma, zeta;
 };
 #define QE(col, r) fe_load(q.E + (uint64_t)(col) * q.n4 + (((r) + row) & (q.n4 - 1)))
-#define QF(col) fe_load(q.F + (uint64_t)(col) * q.n4 + row)
+#define QF(col) fe_load(q.F + (uint64_t)(col) * q.f_stride + ((uint64_t)row * q.f_rs + q.f_ro))
 
 __global__ void k_quotient_gates(const QArgs q) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, grp = blockIdx.y;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, grp = blockIdx.y + q.grp_base;
     if (row >= q.n4) return;
     fr_t acc = fe_zero<FR>();
     const uint32_t c0 = grp * q.cols_per_group, c1 = min(c0 + q.cols_per_group, q.n_gate + q.n_rlc);
@@ -306,7 +310,7 @@ __global__ void k_quotient_gates(const QArgs q) {
         }
         acc = add(acc, mul(e, fe_load(q.ypow + (q.NE - 1 - c))));
     }
-    fe_store(q.part + (uint64_t)grp * q.n4 + row, acc);
+    fe_store(q.part + (uint64_t)blockIdx.y * q.n4 + row, acc);
 }
 
 __device__ __forceinline__ fr_t perm_col_ext(const QArgs& q, uint32_t c, uint32_t row) {
@@ -315,7 +319,7 @@ __device__ __forceinline__ fr_t perm_col_ext(const QArgs& q, uint32_t c, uint32_
 // expression indices: Bp+0: l0(1-Z0); Bp+1: l_last(Zm^2-Zm); Bp+1+j (j=1..m-1): l0(Z_j - Z_{j-1}(w^last X));
 // Bp+1+m+j: l_active(Z_j(wX) prod(v+beta*sigma+gamma) - Z_j(X) prod(v+beta*delta^c*X+gamma))
 __global__ void k_quotient_perm(const QArgs q, uint32_t part_base) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y + q.perm_base;
     if (row >= q.n4) return;
     const uint32_t Bp = q.n_gate + q.n_rlc, m = q.n_chunks;
     const fr_t one = fe_one<FR>();
@@ -328,7 +332,7 @@ __global__ void k_quotient_perm(const QArgs q, uint32_t part_base) {
         fr_t prev = QE(q.zp_base + j - 1, q.usable * q.rot);
         acc = add(acc, mul(mul(l0, sub(zj, prev)), fe_load(q.ypow + (q.NE - 1 - (Bp + 1 + j)))));
     }
-    fr_t x = mul(q.zeta, fe_load(q.tw_ext + row));
+    fr_t x = mul(q.zeta, fe_load(q.tw_ext + ((uint64_t)row * q.f_rs + q.f_ro)));
     fr_t left = zj_w, right = zj;
     for (uint32_t c = j * PERM_CHUNK; c < min((j + 1) * PERM_CHUNK, q.n_perm); c++) {
         fr_t v = add(perm_col_ext(q, c, row), q.gamma);
@@ -336,12 +340,12 @@ __global__ void k_quotient_perm(const QArgs q, uint32_t part_base) {
         right = mul(right, add(v, mul(mul(q.beta, fe_load(q.delta_pow + c)), x)));
     }
     acc = add(acc, mul(mul(l_act, sub(left, right)), fe_load(q.ypow + (q.NE - 1 - (Bp + 1 + m + j)))));
-    fe_store(q.part + (uint64_t)(part_base + j) * q.n4 + row, acc);
+    fe_store(q.part + (uint64_t)(part_base + blockIdx.y) * q.n4 + row, acc);
 }
 // per lookup l, expressions Bl+5l+{0..4}:
 //  l0(1-Z); l_last(Z^2-Z); l_active(Z(wX)(A'+beta)(S'+gamma) - Z(A+beta)(S+gamma)); l0(A'-S'); l_active(A'-S')(A'-A'(w^-1 X))
 __global__ void k_quotient_lookup(const QArgs q, uint32_t part_base) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y + q.lookup_base;
     if (row >= q.n4) return;
     const uint32_t Bl = q.n_gate + q.n_rlc + 2 * q.n_chunks + 1 + 5 * l;
     const fr_t one = fe_one<FR>();
@@ -357,7 +361,7 @@ __global__ void k_quotient_lookup(const QArgs q, uint32_t part_base) {
     fr_t d = sub(ap, sp);
     acc = add(acc, mul(mul(l0, d), fe_load(q.ypow + (q.NE - 4 - Bl))));
     acc = add(acc, mul(mul(l_act, mul(d, sub(ap, ap_m1))), fe_load(q.ypow + (q.NE - 5 - Bl))));
-    fe_store(q.part + (uint64_t)(part_base + l) * q.n4 + row, acc);
+    fe_store(q.part + (uint64_t)(part_base + blockIdx.y) * q.n4 + row, acc);
 }
 // h_ext[row] = (sum_g part[g][row]) / (X^n - 1); X^n - 1 takes 4 values on the extended coset
 __global__ void k_quotient_finish(const fr_t* part, uint32_t groups, uint32_t n4, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
@@ -367,6 +371,33 @@ __global__ void k_quotient_finish(const fr_t* part, uint32_t groups, uint32_t n4
     for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * n4 + row));
     const uint32_t r = row & 3;
     fe_store(h_ext + row, mul(acc, r == 0 ? zh0 : r == 1 ? zh1 : r == 2 ? zh2 : zh3));
+}
+
+// Sharded quotient (one coset of H per shard):
+// out[c][i] = in[c][i] * g^i  -- the coset shift in front of a plain n-point NTT, E_coset[i] = P(g * w^i), g = zeta * w_ext^coset
+__global__ void k_shift_scale(const fr_t* in, uint64_t in_stride, fr_t* out, uint64_t out_stride, const fr_t* gpow, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (i >= n) return;
+    fe_store(out + (uint64_t)c * out_stride + i, mul(fe_load(in + (uint64_t)c * in_stride + i), fe_load(gpow + i)));
+}
+// out[row] = sum_g part[g][row]: one shard's share of the numerator on its coset
+__global__ void k_quotient_partial_sum(const fr_t* part, uint32_t groups, uint32_t n, fr_t* out) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    fr_t acc = fe_zero<FR>();
+    for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * n + row));
+    fe_store(out + row, acc);
+}
+// h_ext[4 i + c] = zh[c] * sum over the shards v that worked on coset c of gathered[v][i]
+struct ShardMap { uint32_t G; uint8_t coset[64]; };
+__global__ void k_quotient_assemble(const fr_t* gathered, ShardMap m, uint32_t n, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (n << EXT_SHIFT)) return;
+    const uint32_t c = e & ((1u << EXT_SHIFT) - 1), i = e >> EXT_SHIFT;
+    fr_t acc = fe_zero<FR>();
+    for (uint32_t v = 0; v < m.G; v++)
+        if (m.coset[v] == c) acc = add(acc, fe_load(gathered + (uint64_t)v * n + i));
+    fe_store(h_ext + e, mul(acc, c == 0 ? zh0 : c == 1 ? zh1 : c == 2 ? zh2 : zh3));
 }
 
 // ---- evaluations and linear combinations ----------------------------------------------------------
@@ -472,6 +503,8 @@ struct zkfhe_prover {
     int stage = 0;
     uint32_t C_all = 0, ap_base = 0, zp_base = 0, zl_base = 0, r_col = 0, lookup_adv_base = 0;
     fr_t *P = nullptr, *E = nullptr, *inst = nullptr, *inst_ext = nullptr, *blind = nullptr, *misc = nullptr;
+    fr_t* gpow = nullptr;        // [4][n] powers of the coset shifts zeta * w_ext^c (sharded quotient only; built on first use)
+    bool gpow_ready[1u << zkfhe::EXT_SHIFT] = {false, false, false, false};
     Fr gamma_rlc, theta, beta, gamma, y, x;
     // host wall-clock at the end of each round (every round ends with a synchronising commitment
     // read-back, so these are true round latencies): [0] phase-0 commit, [1] phase-1 advice,
@@ -491,13 +524,35 @@ namespace zkfhe {
 
 static inline fr_t dev(const Fr& a) { fr_t r; memcpy(r.v, a.l, 32); return r; }
 
+// powers g^i, i < n, of the shift of coset c of the extended domain (g = zeta * w_ext^c), cached in the prover
+static int pr_coset_powers(zkfhe_prover* pr, uint32_t c) {
+    zkfhe_ctx* ctx = pr->ctx;
+    const uint32_t n = pr->pk->n;
+    if (!pr->gpow) ZK_CUDA(ctx, cudaMalloc(&pr->gpow, ((size_t)n << EXT_SHIFT) * 32));
+    if (pr->gpow_ready[c]) return ZKFHE_OK;
+    const Fr g = host::mul(host::to_mont(host::FR_ZETA_CANON), host::pow_u64(host::omega(pr->pk->k + EXT_SHIFT), c));
+    k_powers<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pr->gpow + (size_t)c * n, dev(g), n);
+    ZK_CHECK_LAUNCH(ctx);
+    pr->gpow_ready[c] = true;
+    return ZKFHE_OK;
+}
+
 // commit `count` Lagrange-basis (basis 1) or coefficient-basis (basis 0) columns and write the points
 // (`small_values`: the columns hold witness cells / lookup inputs, mostly far below the field size)
 static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count, int basis, int small_values = 0) {
     zkfhe_ctx* ctx = pr->ctx;
+    // the columns of a phase are independent: shard v commits the contiguous block [v * per, (v + 1) * per) and the
+    // 64-byte points are all-gathered in column order, so every rank feeds the same bytes to its transcript
+    const Shards sh = shards_of(ctx);
+    const uint32_t per = shard_per(count, sh.G);
     g1_affine* d_pts;
-    ZK_TRY(ws_get(ctx, "pr_points", (size_t)count * sizeof(g1_affine), (void**)&d_pts));
-    ZK_TRY(msm_run(ctx, d_cols, pr->pk->n, pr->pk->k, count, basis, d_pts, small_values));
+    ZK_TRY(ws_get(ctx, "pr_points", (size_t)per * sh.G * sizeof(g1_affine), (void**)&d_pts));
+    for (uint32_t v = sh.first; v < sh.last; v++) {
+        uint32_t lo, hi;
+        shard_range(count, sh.G, v, &lo, &hi);
+        if (hi > lo) ZK_TRY(msm_run(ctx, d_cols + (size_t)lo * pr->pk->n, pr->pk->n, pr->pk->k, hi - lo, basis, d_pts + lo, small_values));
+    }
+    ZK_TRY(comm_allgather(ctx, d_pts, (size_t)per * sizeof(g1_affine)));
     ZK_TRY(points_to_canonical(ctx, d_pts, count));
     std::vector<std::array<uint64_t, 8>> h(count);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pts, (size_t)count * 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -539,7 +594,7 @@ void zkfhe_prover_free(zkfhe_prover* pr) {
     if (!pr) return;
     cudaSetDevice(pr->ctx->device);
     cudaStreamSynchronize(pr->ctx->stream);
-    fr_t* bufs[] = {pr->P, pr->E, pr->inst, pr->inst_ext, pr->blind, pr->misc};
+    fr_t* bufs[] = {pr->P, pr->E, pr->inst, pr->inst_ext, pr->blind, pr->misc, pr->gpow};
     for (auto b : bufs) if (b) cudaFree(b);
     delete pr;
 }
@@ -733,11 +788,9 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     fr_t* h_ext = pr->misc;                       // [4n]
     fr_t* h_coef = pr->misc + n4;                 // [4n] -> pieces h_0..h_2 in the first 3n
     {
-        // coefficient form of everything (Lagrange values are no longer needed), then the extended coset
+        // coefficient form of everything (Lagrange values are no longer needed)
         ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->P, n, k, pr->C_all, 1, 0));
         ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst, n, k, 1, 1, 0));
-        ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->E, n4, k4, pr->C_all, 0, 1));
-        ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst_ext, n4, k4, 1, 0, 1));
         const uint32_t NE = n_gate + pk->n_rlc + 2 * pk->n_chunks + 1 + 5 * pk->n_lookup;
         std::vector<Fr> ypow(NE);
         ypow[0] = host::FR_ONE;
@@ -746,7 +799,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_CUDA(ctx, cudaMemcpyAsync(d_ypow, ypow.data(), (size_t)NE * 32, cudaMemcpyHostToDevice, ctx->stream));
         QArgs q{};
         q.E = pr->E; q.F = pk->fixed_ext; q.inst_ext = pr->inst_ext; q.tw_ext = dom4->tw_fwd; q.ypow = d_ypow;
-        q.delta_pow = pk->delta_pow; q.n4 = n4; q.rot = 1u << EXT_SHIFT;
+        q.delta_pow = pk->delta_pow; q.f_stride = n4;
         q.n_gate = n_gate; q.n_rlc = pk->n_rlc; q.rlc_base = n_gate; q.n_advice = pk->n_advice; q.n_lookup = pk->n_lookup;
         q.n_chunks = pk->n_chunks; q.n_perm = pk->n_perm; q.NE = NE; q.zp_base = pr->zp_base; q.zl_base = pr->zl_base;
         q.ap_base = pr->ap_base; q.lookup_adv_base = pr->lookup_adv_base; q.usable = usable;
@@ -756,25 +809,82 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         q.gamma_rlc = dev(pr->gamma_rlc); q.beta = dev(pr->beta); q.gamma = dev(pr->gamma);
         q.zeta = dev(host::to_mont(host::FR_ZETA_CANON));
         const uint32_t g_gate = (n_gate + pk->n_rlc + q.cols_per_group - 1) / q.cols_per_group;
-        const uint32_t groups = g_gate + pk->n_chunks + pk->n_lookup;
-        fr_t* part;
-        ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)groups * n4 * 32, (void**)&part));
-        q.part = part;
-        const uint32_t bx = (n4 + 127) / 128;
-        k_quotient_gates<<<dim3(bx, g_gate), 128, 0, ctx->stream>>>(q);
-        ZK_CHECK_LAUNCH(ctx);
-        k_quotient_perm<<<dim3(bx, pk->n_chunks), 128, 0, ctx->stream>>>(q, g_gate);
-        ZK_CHECK_LAUNCH(ctx);
-        if (pk->n_lookup) {
-            k_quotient_lookup<<<dim3(bx, pk->n_lookup), 128, 0, ctx->stream>>>(q, g_gate + pk->n_chunks);
-            ZK_CHECK_LAUNCH(ctx);
-        }
         // 1 / (X^n - 1) on zeta * w_ext^j: X^n = zeta^n * (w_ext^n)^j, w_ext^n is a primitive 4th root of unity
         Fr zeta = host::to_mont(host::FR_ZETA_CANON), zn = host::pow_u64(zeta, n), i4 = host::pow_u64(host::omega(k4), n);
         Fr zh[4], cur = zn;
         for (int r = 0; r < 4; r++) { zh[r] = host::inv(host::sub(cur, host::FR_ONE)); cur = host::mul(cur, i4); }
-        k_quotient_finish<<<bx, 128, 0, ctx->stream>>>(part, groups, n4, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
-        ZK_CHECK_LAUNCH(ctx);
+        const Shards sh = shards_of(ctx);
+        if (sh.G == 1) {
+            // one GPU: the whole extended coset zeta * H_ext at once
+            ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->E, n4, k4, pr->C_all, 0, 1));
+            ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst_ext, n4, k4, 1, 0, 1));
+            q.n4 = n4; q.rot = 1u << EXT_SHIFT; q.f_rs = 1; q.f_ro = 0;
+            const uint32_t groups = g_gate + pk->n_chunks + pk->n_lookup;
+            fr_t* part;
+            ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)groups * n4 * 32, (void**)&part));
+            q.part = part;
+            const uint32_t bx = (n4 + 127) / 128;
+            k_quotient_gates<<<dim3(bx, g_gate), 128, 0, ctx->stream>>>(q);
+            ZK_CHECK_LAUNCH(ctx);
+            k_quotient_perm<<<dim3(bx, pk->n_chunks), 128, 0, ctx->stream>>>(q, g_gate);
+            ZK_CHECK_LAUNCH(ctx);
+            if (pk->n_lookup) {
+                k_quotient_lookup<<<dim3(bx, pk->n_lookup), 128, 0, ctx->stream>>>(q, g_gate + pk->n_chunks);
+                ZK_CHECK_LAUNCH(ctx);
+            }
+            k_quotient_finish<<<bx, 128, 0, ctx->stream>>>(part, groups, n4, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
+            ZK_CHECK_LAUNCH(ctx);
+        } else {
+            // several GPUs: zeta * H_ext is the union of the four cosets g_c * H, g_c = zeta * w_ext^c (extended index
+            // 4 i + c), and rotations stay inside a coset.  Shard v works on coset v mod 4; when more than four shards
+            // exist, the shards of one coset split the expression list (gate groups, permutation chunks, lookups)
+            // between them.  Each shard leaves n partial numerator values; one all-gather; every rank then sums the
+            // shares of each coset, divides by X^n - 1 and interleaves.
+            const uint32_t NC = 1u << EXT_SHIFT;
+            // work slots: slot s is coset s mod 4; with more than four shards the slots of one coset split the
+            // expression list between them.  Shard v owns slots v, v + G, ... (exactly slot v once G >= 4).
+            const uint32_t S = sh.G < NC ? NC : sh.G;
+            ShardMap map{};
+            map.G = S;
+            uint32_t halves[1u << EXT_SHIFT] = {0, 0, 0, 0}, half_of[64];
+            for (uint32_t t = 0; t < S; t++) { map.coset[t] = (uint8_t)(t % NC); half_of[t] = halves[t % NC]++; }
+            fr_t* gathered;      // [S][n]
+            ZK_TRY(ws_get(ctx, "pr_qgather", (size_t)S * n * 32, (void**)&gathered));
+            const uint32_t bx = (n + 127) / 128;
+            for (uint32_t v = sh.first; v < sh.last; v++)
+                for (uint32_t t = v; t < S; t += sh.G) {
+                    const uint32_t c = map.coset[t], H = halves[c], hidx = half_of[t];
+                    ZK_TRY(pr_coset_powers(pr, c));
+                    const fr_t* gpow = pr->gpow + (size_t)c * n;
+                    k_shift_scale<<<dim3((n + 255) / 256, pr->C_all), 256, 0, ctx->stream>>>(pr->P, n, pr->E, n, gpow, n);
+                    ZK_CHECK_LAUNCH(ctx);
+                    k_shift_scale<<<dim3((n + 255) / 256, 1), 256, 0, ctx->stream>>>(pr->inst, n, pr->inst_ext, n, gpow, n);
+                    ZK_CHECK_LAUNCH(ctx);
+                    ZK_TRY(ntt_run(ctx, pr->E, n, n, pr->E, n, k, pr->C_all, 0, 0));
+                    ZK_TRY(ntt_run(ctx, pr->inst_ext, n, n, pr->inst_ext, n, k, 1, 0, 0));
+                    q.n4 = n; q.rot = 1; q.f_rs = NC; q.f_ro = c;
+                    uint32_t glo, ghi, plo, phi, llo, lhi;
+                    shard_range(g_gate, H, hidx, &glo, &ghi);
+                    shard_range(pk->n_chunks, H, hidx, &plo, &phi);
+                    shard_range(pk->n_lookup, H, hidx, &llo, &lhi);
+                    const uint32_t groups = (ghi - glo) + (phi - plo) + (lhi - llo);
+                    fr_t* part;
+                    ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)(groups + 1) * n * 32, (void**)&part));
+                    q.part = part; q.grp_base = glo; q.perm_base = plo; q.lookup_base = llo;
+                    if (ghi > glo) { k_quotient_gates<<<dim3(bx, ghi - glo), 128, 0, ctx->stream>>>(q); ZK_CHECK_LAUNCH(ctx); }
+                    if (phi > plo) { k_quotient_perm<<<dim3(bx, phi - plo), 128, 0, ctx->stream>>>(q, ghi - glo); ZK_CHECK_LAUNCH(ctx); }
+                    if (lhi > llo) { k_quotient_lookup<<<dim3(bx, lhi - llo), 128, 0, ctx->stream>>>(q, (ghi - glo) + (phi - plo)); ZK_CHECK_LAUNCH(ctx); }
+                    k_quotient_partial_sum<<<bx, 128, 0, ctx->stream>>>(part, groups, n, gathered + (size_t)t * n);
+                    ZK_CHECK_LAUNCH(ctx);
+                }
+            if (ctx->nccl_comm)
+                for (uint32_t base = 0; base < S; base += sh.G) {        // one all-gather per round of slots (one in all when G >= 4)
+                    if (base + sh.G > S) return fail(ctx, ZKFHE_ERR_ARG, "prove: %u ranks do not divide the %u cosets of the extended domain", sh.G, NC);
+                    ZK_TRY(comm_allgather(ctx, gathered + (size_t)base * n, (size_t)n * 32));
+                }
+            k_quotient_assemble<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(gathered, map, n, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
+            ZK_CHECK_LAUNCH(ctx);
+        }
         ZK_CUDA(ctx, cudaMemcpyAsync(h_coef, h_ext, (size_t)n4 * 32, cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_TRY(ntt_run(ctx, h_coef, n4, n4, h_coef, n4, k4, 1, 1, 1));
         ZK_TRY(commit_and_write(pr, h_coef, 3, 0));
