@@ -302,7 +302,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transcript", type=int, default=1, help="1 Poseidon (default: the reference's transcript), 0 BLAKE2b")
-    ap.add_argument("--streams", type=int, default=8, help="proofs in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-over-N-GPUs latency measurement")
+    ap.add_argument("--streams", type=int, default=16, help="proofs in flight per GPU (one CUDA stream + host thread each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -470,6 +471,22 @@ def main():
     mb_ms, mb_ops = ctx.microbench(0, 2000)
     peak_products = mb_ops / (mb_ms * 1e-3)
 
+    # ---- N > 1: ONE proof over all N GPUs (strong scaling of the single-proof latency) ----
+    # The throughput number above keeps whole proofs per GPU (no data-path collective).  This is the other split: the
+    # library shards the commitment phases by column and the quotient by coset behind zkfhe_prove_*; measured after the
+    # timed region, on fresh contexts, and checked to give the single-GPU proof bytes on every rank.
+    sharded_res = None
+    if world > 1 and not args.no_sharded:
+        from zk_fhe_b200 import sharded
+        for ps in streams[1:]:
+            ps.ctx.sync()
+        sharded_res = {}
+        for label, kk, tk in (("k13_poseidon", 13, 1), ("k13_blake2b", 13, 0), ("k16_poseidon", 16, 1), ("k16_blake2b", 16, 0)):
+            try:
+                sharded_res[label] = sharded.run(kk, 5 if kk == 13 else 3, tk, dist, rank, world, local_rank)
+            except Exception as e:           # a failed extra must not lose the headline line
+                sharded_res[label] = {"error": repr(e)[:300]}
+
     if rank == 0:
         peak, peak_kind = peaks()
         ms_per_step = total_ms / args.steps
@@ -513,6 +530,8 @@ def main():
                               "msm_sort_reduce_ms": red_ms / lat_steps, "ntt_ms": ntt_ms / lat_steps,
                               "other_ms": lat_ms - (acc_ms + ntt_ms + red_ms) / lat_steps},
         }
+        if sharded_res is not None:
+            line["sharded_single_proof"] = sharded_res
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_arm(2, 1, budget_s=30.0)
         print(json.dumps(line))

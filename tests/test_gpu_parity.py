@@ -220,6 +220,49 @@ def test_msm_small_value_hint_gives_identical_points(ctx):
         assert np.array_equal(got, want), f"small_values={small}"
 
 
+def test_msm_runs_of_equal_scalars_go_through_the_prefix_table(ctx):
+    """Runs of equal scalars are committed as prefix[b+1] - prefix[a] of the basis (two references per window
+    instead of one per row): runs at both ends of the column, runs of length 2, full-size values repeated, runs of
+    zeros, a column that is one single run, runs touching each other, with and without the small-value hint."""
+    import torch
+    k, n = 13, 1 << 13
+    _, gl = toy_srs(k)
+    ctx.load_srs(k, g=None, g_lagrange=gl)
+    pyr = random.Random(77)
+    big = [pyr.randrange(field.R_MOD) for _ in range(8)]
+
+    def runs(lengths, values):
+        out = []
+        for i in range(10 ** 9):
+            if len(out) >= n:
+                return out[:n]
+            out += [values[i % len(values)]] * lengths[i % len(lengths)]
+
+    cols = [runs([3000, 1, 2, 5000, 7], big),                      # the shape of a grand-product column
+            runs([2], big[:3]),                                    # every run has length 2
+            runs([1, 2, 1, 3], [0, 5, 0, 0, 9, 1]),                # runs of zeros between short runs
+            runs([n], [big[0]]),                                   # one run
+            runs([1], big),                                        # no runs at all
+            runs([n - 1, 1], [big[1], big[2]]),                    # run up to the last row but one
+            runs([1, n - 1], [big[3], big[4]]),                    # run from row 1 to the end
+            runs([17, 4000], [1, 2, field.R_MOD - 1])]
+    scal = np.ascontiguousarray(np.concatenate([fr_to_mont_array(c) for c in cols]))
+    want = cbind.msm(scal, gl, n, len(cols))
+    d = torch.from_numpy(scal.view(np.int64).reshape(-1)).cuda()
+    out = torch.zeros(len(cols) * 8, dtype=torch.int64, device="cuda")
+    for small in (False, True):
+        out.zero_()
+        ctx.msm_g1_dev(d.data_ptr(), len(cols), 1, out.data_ptr(), small_values=small)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(len(cols), 8), want), f"small_values={small}"
+    # one column alone and three columns: the cluster sort path of the few-column commits
+    for lo, cnt in ((0, 1), (3, 3)):
+        out.zero_()
+        ctx.msm_g1_dev(d.data_ptr() + lo * n * 32, cnt, 1, out.data_ptr())
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(len(cols), 8)[:cnt], want[lo:lo + cnt])
+
+
 def test_msm_k16_long_skewed_columns_match_oracle(ctx):
     """2^16-scalar columns (config 3/4 size): the cluster counting sort and the multi-level combine of hot buckets
     (0/1-valued and constant columns put tens of thousands of references into one bucket), with and without the
@@ -267,19 +310,6 @@ def test_srs_setup_on_gpu_matches_oracle(ctx):
     for basis, bases in ((0, og), (1, ogl)):
         assert c2.msm_g1(sc, 1, basis=basis) == cbind.msm(sc, bases, 1 << k, 1).tobytes()
     c2.close()
-
-
-def test_commit_columns_sharded_single_rank_equals_plain_msm(ctx):
-    """zk_fhe_b200.dist.commit_columns_sharded (the column-sharded commit phase) at world size 1."""
-    import torch
-    from zk_fhe_b200 import dist as zd
-    k, n, cols = 8, 256, 5
-    g, gl = toy_srs(k)
-    ctx.load_srs(k, g=g, g_lagrange=gl)
-    sc = random_fr_mont(np.random.default_rng(8), cols * n)
-    d = torch.from_numpy(sc.view(np.int64)).cuda()
-    got = zd.commit_columns_sharded(ctx, d, cols, basis=1).cpu().numpy().tobytes()
-    assert got == cbind.msm(sc, gl, n, cols).tobytes()
 
 
 def test_fr_convert_roundtrip(ctx):

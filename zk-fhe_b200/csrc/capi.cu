@@ -409,7 +409,7 @@ int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t
     for (int which = 0; which < 2; which++) {
         if (!src[which]) continue;
         ZK_CUDA(ctx, cudaMemcpyAsync(d, src[which], bytes, cudaMemcpyHostToDevice, ctx->stream));
-        ZK_TRY(msm_load_basis(ctx, which, (const g1_affine*)d, k));
+        ZK_TRY(msm_load_basis(ctx, which, (const g1_affine*)d, k, which == 1));
     }
     ctx->srs_k = k;
     return ZKFHE_OK;
@@ -425,8 +425,8 @@ int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t
     fr_t tau;
     memcpy(&tau, h_tau_fr, 32);
     ZK_TRY(srs_setup(ctx, k, tau, d, d + ((size_t)1 << k)));
-    ZK_TRY(msm_load_basis(ctx, 0, d, k));
-    ZK_TRY(msm_load_basis(ctx, 1, d + ((size_t)1 << k), k));
+    ZK_TRY(msm_load_basis(ctx, 0, d, k, false));
+    ZK_TRY(msm_load_basis(ctx, 1, d + ((size_t)1 << k), k, true));
     ctx->srs_k = k;
     if (h_g_out) ZK_CUDA(ctx, cudaMemcpyAsync(h_g_out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_g_lagrange_out)

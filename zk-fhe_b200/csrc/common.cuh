@@ -28,6 +28,11 @@ struct MsmBasis {
     // reduce per column instead of 4096, and the bucket reduction is what such columns pay for
     g1_affine* table_s = nullptr;
     uint32_t c_s = 0, W_s = 0;
+    // prefix sums behind each table (Lagrange basis only): entry W*n + w*(n+1) + i of the same allocation holds
+    // sum_{j<i} table[w*n + j], so a run of equal scalars over rows [a, b] costs two references per window
+    // (+prefix[b+1], -prefix[a]) instead of b - a + 1.  Grand-product columns are constant over thousands of rows
+    // wherever a permutation chunk has no copy-constrained cell, and 0/1 witness columns are full of runs.
+    bool prefix = false;
     bool loaded = false;
     bool shared = false;          // table owned by another context (zkfhe_share_srs)
 };
@@ -150,7 +155,7 @@ inline int ws_get(zkfhe_ctx* ctx, const char* name, size_t bytes, void** out) {
 int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out);
 int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_len, fr_t* d_out,
             uint64_t out_stride, uint32_t log_n, uint32_t batch, int inverse, int coset);
-int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n);
+int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n, bool prefix);
 int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log_n, uint32_t batch,
             int which, g1_affine* d_out, int small_values = 0);
 int srs_setup(zkfhe_ctx* ctx, uint32_t log_n, const fr_t& tau_mont, g1_affine* d_g, g1_affine* d_gl);

@@ -36,6 +36,8 @@ namespace zkfhe {
 // (small-valued columns have a few references per scalar: short slices keep enough threads in flight)
 static inline uint32_t pick_seg(uint32_t batch, bool narrow) { return batch < 32 || narrow ? 16 : 64; }
 
+__device__ __noinline__ void xyzz_add_ni2(g1_xyzz& acc, const g1_xyzz& p) { xyzz_add(acc, p); }
+
 // ---- fixed-base table ---------------------------------------------------------------------
 __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint32_t n, uint32_t c, uint32_t W) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +53,47 @@ __global__ void k_msm_precompute(const g1_affine* bases, g1_affine* table, uint3
         affine_store(table + (size_t)w * n + i, a);
         q = xyzz_from_affine(a);     // keep Z = 1 so the next doublings stay cheap
     }
+}
+
+// Prefix sums of one window row of the table, prefix[w][i] = sum_{j<i} table[w][j], i <= n (affine; prefix[w][0] is the
+// identity).  Three launches: chunk totals, a serial scan of the totals per window, the prefixes inside each chunk.
+static constexpr uint32_t PFX_CHUNK = 32;
+__global__ void k_msm_prefix_totals(const g1_affine* table, uint32_t n, uint32_t W, g1_xyzz* totals) {
+    const uint32_t chunks = (n + PFX_CHUNK - 1) / PFX_CHUNK;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * W) return;
+    const uint32_t w = t / chunks, ch = t % chunks;
+    const g1_affine* row = table + (size_t)w * n;
+    g1_xyzz acc = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t i = ch * PFX_CHUNK; i < min((ch + 1) * PFX_CHUNK, n); i++) xyzz_madd(acc, affine_load(row + i), false);
+    xyzz_store(totals + t, acc);
+}
+__global__ void k_msm_prefix_scan(g1_xyzz* totals, uint32_t chunks, uint32_t W) {     // exclusive scan, one thread per window
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    g1_xyzz run = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t ch = 0; ch < chunks; ch++) {
+        g1_xyzz t = xyzz_load(totals + (size_t)w * chunks + ch);
+        xyzz_store(totals + (size_t)w * chunks + ch, run);
+        xyzz_add_ni2(run, t);
+    }
+}
+__global__ void k_msm_prefix_fill(const g1_affine* table, uint32_t n, uint32_t W, const g1_xyzz* totals, g1_affine* prefix) {
+    const uint32_t chunks = (n + PFX_CHUNK - 1) / PFX_CHUNK;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks * W) return;
+    const uint32_t w = t / chunks, ch = t % chunks;
+    const g1_affine* row = table + (size_t)w * n;
+    g1_affine* out = prefix + (size_t)w * (n + 1);
+    g1_xyzz acc = xyzz_load(totals + t);
+#pragma unroll 1
+    for (uint32_t i = ch * PFX_CHUNK; i < min((ch + 1) * PFX_CHUNK, n); i++) {
+        affine_store(out + i, xyzz_to_affine(acc));              // prefix[i] excludes point i
+        xyzz_madd(acc, affine_load(row + i), false);
+    }
+    if (ch + 1 == chunks) affine_store(out + n, xyzz_to_affine(acc));
 }
 
 // ---- digit recoding -----------------------------------------------------------------------
@@ -88,6 +131,28 @@ __device__ __forceinline__ void for_each_digit(const fr_t& s_canon, uint32_t c, 
     if (w < W) emit((uint32_t)buf & mask);          // the last, short window
 }
 
+// The references of scalar i of a column: f(table index, bucket, negative) for every non-zero digit.  With a prefix
+// table behind the window table (ps_base != 0) a run of equal scalars over rows [a, b] is emitted at its two ends only:
+// -prefix[w][a] at row a and +prefix[w][b + 1] at row b, since sum_{a<=i<=b} 2^(cw) P_i = prefix[w][b+1] - prefix[w][a];
+// the rows in between emit nothing.  Both passes of the counting sort call this, so they agree by construction.
+template <class Fn>
+__device__ __forceinline__ void for_each_ref(const fr_t* sc, uint32_t i, uint32_t n, uint32_t c, uint32_t W, uint32_t ps_base, Fn f) {
+    const fr_t raw = fe_load(sc + i);
+    if (is_zero(raw)) return;
+    uint32_t kind = 0;                                    // 0 alone, 1 first row of a run, 2 last row, 3 interior
+    if (ps_base) {
+        if (i > 0 && eq(raw, fe_load(sc + i - 1))) kind |= 2;
+        if (i + 1 < n && eq(raw, fe_load(sc + i + 1))) kind |= 1;
+        if (kind == 3) return;
+    }
+    const fr_t s = from_mont(raw);
+    for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
+        if (kind == 0) f(w * n + i, b, negative);
+        else if (kind == 1) f(ps_base + w * (n + 1) + i, b, !negative);
+        else f(ps_base + w * (n + 1) + i + 1, b, negative);
+    });
+}
+
 // One CTA per column: histogram -> exclusive scans -> scatter (counting sort by bucket).
 //   bucket_off[col][NB+1] : start of each bucket in sorted[col]; bucket_off[NB] = number of references
 //   rank[col][NB+1]       : number of non-empty buckets before bucket b
@@ -97,7 +162,7 @@ extern __shared__ uint32_t msm_smem[];
 __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
                                                    uint32_t W, uint32_t* bucket_off, uint32_t* rank_out,
                                                    uint32_t* sorted, uint64_t sorted_stride, uint32_t skew_limit,
-                                                   uint32_t* skew_out) {
+                                                   uint32_t* skew_out, uint32_t ps_base) {
     const uint32_t NB = 1u << (c - 1);
     uint32_t* cnt = msm_smem;                 // [NB] counts, then running cursors
     __shared__ uint32_t warp_tot[2][32];
@@ -109,10 +174,8 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
 
     for (uint32_t b = tid; b < NB; b += nt) cnt[b] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += nt) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s, c, W, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
-    }
+    for (uint32_t i = tid; i < n; i += nt)
+        for_each_ref(sc, i, n, c, W, ps_base, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
     __syncthreads();
 
     // exclusive scans of the counts (entries) and of the non-empty flags (ranks)
@@ -165,13 +228,11 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
     if (tid == nt - 1) { boff[NB] = run_e; rnk[NB] = run_s; }
     __syncthreads();
 
-    for (uint32_t i = tid; i < n; i += nt) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
+    for (uint32_t i = tid; i < n; i += nt)
+        for_each_ref(sc, i, n, c, W, ps_base, [&](uint32_t ref, uint32_t b, bool negative) {
             uint32_t pos = atomicAdd(&cnt[b], 1u);
-            out[pos] = (w * n + i) | (negative ? 0x80000000u : 0u);
+            out[pos] = ref | (negative ? 0x80000000u : 0u);
         });
-    }
 }
 
 // The same counting sort spread over a thread-block CLUSTER of SORT_CS CTAs per column (distributed shared memory):
@@ -184,7 +245,8 @@ __global__ void __launch_bounds__(1024) k_msm_sort(const fr_t* scalars, uint64_t
 static constexpr uint32_t SORT_CS = 8;
 __global__ void __cluster_dims__(SORT_CS, 1, 1) __launch_bounds__(1024)
 k_msm_sort_cluster(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c, uint32_t W, uint32_t* bucket_off,
-                   uint32_t* rank_out, uint32_t* sorted, uint64_t sorted_stride, uint32_t skew_limit, uint32_t* skew_out) {
+                   uint32_t* rank_out, uint32_t* sorted, uint64_t sorted_stride, uint32_t skew_limit, uint32_t* skew_out,
+                   uint32_t ps_base) {
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t NB = 1u << (c - 1);
     uint32_t* cnt = msm_smem;                 // [NB] this CTA's histogram, then its scatter cursors
@@ -200,10 +262,8 @@ k_msm_sort_cluster(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
 
     for (uint32_t b = tid; b < NB; b += nt) cnt[b] = 0;
     __syncthreads();
-    for (uint32_t i = i0 + tid; i < i1; i += nt) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s, c, W, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
-    }
+    for (uint32_t i = i0 + tid; i < i1; i += nt)
+        for_each_ref(sc, i, n, c, W, ps_base, [&](uint32_t, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
     cluster.sync();
 
     // bucket slice of this CTA: totals over the CS histograms, exclusive scans inside the slice
@@ -280,13 +340,11 @@ k_msm_sort_cluster(const fr_t* scalars, uint64_t stride, uint32_t n, uint32_t c,
     if (q == 0 && tid == 0) { boff[NB] = all_e; rnk[NB] = all_s; skew_out[col] = skewed ? 1u : 0u; }
     cluster.sync();                                             // every cursor is in place (and no DSMEM access after this)
 
-    for (uint32_t i = i0 + tid; i < i1; i += nt) {
-        fr_t s = from_mont(fe_load(sc + i));
-        for_each_digit(s, c, W, [&](uint32_t w, uint32_t b, bool negative) {
+    for (uint32_t i = i0 + tid; i < i1; i += nt)
+        for_each_ref(sc, i, n, c, W, ps_base, [&](uint32_t ref, uint32_t b, bool negative) {
             uint32_t pos = atomicAdd(&cnt[b], 1u);
-            out[pos] = (w * n + i) | (negative ? 0x80000000u : 0u);
+            out[pos] = ref | (negative ? 0x80000000u : 0u);
         });
-    }
 }
 
 // Thread t of a column sums references [t*SEG, (t+1)*SEG) of the bucket-sorted list with mixed XYZZ
@@ -593,7 +651,28 @@ static uint32_t pick_window(uint32_t log_n) {
     return c;
 }
 
-int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n) {
+// window table (+ prefix sums behind it) of one expansion: table[w*n + i] = 2^(c*w) P_i
+static int build_table(zkfhe_ctx* ctx, const g1_affine* d_bases, size_t n, uint32_t c, uint32_t W, bool prefix, g1_affine** out) {
+    const size_t entries = n * W + (prefix ? (n + 1) * W : 0);
+    if (entries >= (1ull << 31)) return fail(ctx, ZKFHE_ERR_ARG, "msm: %zu table entries do not fit 31 bits", entries);
+    ZK_CUDA(ctx, cudaMalloc(out, entries * sizeof(g1_affine)));
+    k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, *out, (uint32_t)n, c, W);
+    ZK_CHECK_LAUNCH(ctx);
+    if (prefix) {
+        const uint32_t chunks = (uint32_t)((n + PFX_CHUNK - 1) / PFX_CHUNK);
+        g1_xyzz* totals;
+        ZK_TRY(ws_get(ctx, "msm_pfx_totals", (size_t)chunks * W * sizeof(g1_xyzz), (void**)&totals));
+        k_msm_prefix_totals<<<(chunks * W + 127) / 128, 128, 0, ctx->stream>>>(*out, (uint32_t)n, W, totals);
+        ZK_CHECK_LAUNCH(ctx);
+        k_msm_prefix_scan<<<(W + 31) / 32, 32, 0, ctx->stream>>>(totals, chunks, W);
+        ZK_CHECK_LAUNCH(ctx);
+        k_msm_prefix_fill<<<(chunks * W + 127) / 128, 128, 0, ctx->stream>>>(*out, (uint32_t)n, W, totals, *out + n * W);
+        ZK_CHECK_LAUNCH(ctx);
+    }
+    return ZKFHE_OK;
+}
+
+int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t log_n, bool prefix) {
     MsmBasis& B = ctx->basis[which];
     if (B.table && !B.shared) {
         ZK_CUDA(ctx, cudaFree(B.table));
@@ -603,18 +682,15 @@ int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t
     B.log_n = log_n;
     B.c = pick_window(log_n);
     B.W = (255 + B.c - 1) / B.c;
+    B.prefix = prefix && log_n >= 8;
+    if (const char* e = getenv("ZKFHE_MSM_PREFIX")) B.prefix = B.prefix && atoi(e) != 0;
     size_t n = (size_t)1 << log_n;
-    if (n * B.W >= (1ull << 31)) return fail(ctx, ZKFHE_ERR_ARG, "msm: n*W=%zu does not fit 31 bits", n * B.W);
-    ZK_CUDA(ctx, cudaMalloc(&B.table, n * B.W * sizeof(g1_affine)));
-    k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, B.table, (uint32_t)n, B.c, B.W);
-    ZK_CHECK_LAUNCH(ctx);
+    ZK_TRY(build_table(ctx, d_bases, n, B.c, B.W, B.prefix, &B.table));
     B.c_s = B.W_s = 0;
     if (log_n >= 11) {                   // narrow-window expansion for small-valued columns
         B.c_s = B.c - 3;
         B.W_s = (255 + B.c_s - 1) / B.c_s;
-        ZK_CUDA(ctx, cudaMalloc(&B.table_s, n * B.W_s * sizeof(g1_affine)));
-        k_msm_precompute<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d_bases, B.table_s, (uint32_t)n, B.c_s, B.W_s);
-        ZK_CHECK_LAUNCH(ctx);
+        ZK_TRY(build_table(ctx, d_bases, n, B.c_s, B.W_s, B.prefix, &B.table_s));
     }
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     B.loaded = true;
@@ -628,10 +704,15 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     if (!B.loaded) return fail(ctx, ZKFHE_ERR_STATE, "msm: zkfhe_load_srs has not been called");
     if (log_n != B.log_n) return fail(ctx, ZKFHE_ERR_ARG, "msm: log_n=%u but SRS has k=%u", log_n, B.log_n);
     if (batch == 0) return ZKFHE_OK;
-    const bool narrow = small_values && B.table_s;
+    // the narrow-window table also serves commits of a few columns whatever their values: 30 % more point additions in
+    // a launch that cannot fill the GPU anyway, against an 8x smaller bucket set on the latency-bound reduction
+    bool few = batch <= 4;
+    if (const char* e = getenv("ZKFHE_MSM_FEW_NARROW")) few = few && atoi(e) != 0;
+    const bool narrow = (small_values || few) && B.table_s;
     const g1_affine* table = narrow ? B.table_s : B.table;
     const uint32_t n = 1u << log_n, c = narrow ? B.c_s : B.c, W = narrow ? B.W_s : B.W, NB = 1u << (c - 1);
     const uint64_t max_refs = (uint64_t)n * W;
+    const uint32_t ps_base = B.prefix ? n * W : 0;          // runs of equal scalars are referenced through the prefix table
     const uint32_t SEG = pick_seg(batch, narrow);
     const uint64_t max_thr = (max_refs + SEG - 1) / SEG;     // accumulate threads per column
     const uint64_t max_segs = NB + max_thr;                  // partial slots: rank[b] + t
@@ -699,9 +780,9 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         const fr_t* sc = d_scalars + (uint64_t)done * stride;
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
         if (cluster_sort)
-            k_msm_sort_cluster<<<nb * SORT_CS, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
+            k_msm_sort_cluster<<<nb * SORT_CS, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew, ps_base);
         else
-            k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew);
+            k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew, ps_base);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
@@ -755,7 +836,7 @@ int msm_variable_base(zkfhe_ctx* ctx, const g1_affine* h_points, const fr_t* h_s
     ZK_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars, count * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     const MsmBasis saved = ctx->basis[0];
     ctx->basis[0] = MsmBasis{};
-    int rc = msm_load_basis(ctx, 0, d_pts, log_n);
+    int rc = msm_load_basis(ctx, 0, d_pts, log_n, false);
     if (rc == ZKFHE_OK) rc = msm_run(ctx, d_sc, n, log_n, 1, 0, d_out, 0);
     if (rc == ZKFHE_OK && cudaMemcpyAsync(h_out, d_out, sizeof(g1_affine), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
         rc = fail(ctx, ZKFHE_ERR_CUDA, "msm_variable_base: copy back failed");
