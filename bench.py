@@ -471,22 +471,6 @@ def main():
     mb_ms, mb_ops = ctx.microbench(0, 2000)
     peak_products = mb_ops / (mb_ms * 1e-3)
 
-    # ---- N > 1: ONE proof over all N GPUs (strong scaling of the single-proof latency; SURVEY.md section 8(e)) ----
-    # The throughput number above keeps whole proofs per GPU (no data-path collective).  This is the other split: the
-    # library shards the commitment phases by column and the quotient by coset behind zkfhe_prove_*; measured after the
-    # timed region, on fresh contexts, and checked to give the single-GPU proof bytes on every rank.
-    sharded_res = None
-    if world > 1 and not args.no_sharded:
-        from zk_fhe_b200 import sharded
-        for ps in streams[1:]:
-            ps.ctx.sync()
-        sharded_res = {}
-        for label, kk, tk in (("k13_poseidon", 13, 1), ("k13_blake2b", 13, 0), ("k16_poseidon", 16, 1), ("k16_blake2b", 16, 0)):
-            try:
-                sharded_res[label] = sharded.run(kk, 5 if kk == 13 else 3, tk, dist, rank, world, local_rank)
-            except Exception as e:           # a failed extra must not lose the headline line
-                sharded_res[label] = {"error": repr(e)[:300]}
-
     if rank == 0:
         peak, peak_kind = peaks()
         ms_per_step = total_ms / args.steps
@@ -530,11 +514,38 @@ def main():
                               "msm_sort_reduce_ms": red_ms / lat_steps, "ntt_ms": ntt_ms / lat_steps,
                               "other_ms": lat_ms - (acc_ms + ntt_ms + red_ms) / lat_steps},
         }
-        if sharded_res is not None:
-            line["sharded_single_proof"] = sharded_res
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_reference_arm(2, 1, budget_s=30.0)
-        print(json.dumps(line))
+    # ---- N > 1: ONE proof over all N GPUs (strong scaling of the single-proof latency; SURVEY.md section 8(e)) ----
+    # The throughput number above keeps whole proofs per GPU (no data-path collective).  This is the other split: the
+    # library shards the commitment phases by column and the quotient by coset behind zkfhe_prove_*; measured after the
+    # timed region, on fresh contexts, and checked to give the single-GPU proof bytes on every rank.  It runs under a
+    # watchdog so that a stuck collective can never cost the headline line.
+    hung = False
+    if world > 1 and not args.no_sharded:
+        from zk_fhe_b200 import sharded
+        for ps in streams:
+            ps.ctx.sync()
+        sharded_res = {}
+
+        def measure():
+            for label, kk, tk in (("k13_poseidon", 13, 1), ("k13_blake2b", 13, 0), ("k16_poseidon", 16, 1), ("k16_blake2b", 16, 0)):
+                try:
+                    sharded_res[label] = sharded.run(kk, 5 if kk == 13 else 3, tk, dist, rank, world, local_rank)
+                except Exception as e:
+                    sharded_res[label] = {"error": repr(e)[:300]}
+                    return
+
+        th = threading.Thread(target=measure, daemon=True)
+        th.start()
+        th.join(timeout=300.0)
+        hung = th.is_alive()
+        if rank == 0:
+            line["sharded_single_proof"] = dict(sharded_res, **({"error": "timed out after 300 s"} if hung else {}))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if hung:
+        os._exit(0)                      # do not wait for a communicator that will never come back
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

@@ -16,6 +16,7 @@ TAU = 0x5EED5EED5EED5EED5EED5EED
 def run(k, proofs, transcript, dist, rank, world, local_rank):
     import torch
     from . import capi
+    torch.cuda.set_device(local_rank)          # the caller may be a worker thread: the CUDA device is per thread
     from . import bfv, bfv_py, prover
     from . import dist as zd
     if k == 13:
