@@ -289,13 +289,17 @@ void zkfhe_proof_free(uint8_t* proof);
 
 /* ---- one proof over several GPUs (nothing of the kind exists in the reference) ---------
  * SPMD: every rank holds the same proving key and SRS on its own GPU and makes the SAME sequence of witness / prove
- * calls on the same input and seed.  Inside zkfhe_prove_* each commitment phase is then sharded by column (rank r
- * commits the block zkfhe_shard_range gives it; one ncclAllGather of 64 bytes per column) and the quotient by coset
- * of the extended domain (rank r evaluates the identities on coset r mod 4 -- with more than four ranks the ranks of
- * a coset split the expression list -- and one ncclAllGather moves n x 32 bytes per rank).  Everything else is
- * replicated, so every rank returns the same proof, byte-identical to the single-GPU proof.
- * libnccl.so.2 is loaded with dlopen on first use.  Rank counts 1, 2 and >= 4 are supported (3 does not divide the
- * four cosets). */
+ * calls on the same input and seed.  Inside zkfhe_prove_* the work then splits into one shard per rank:
+ *   - every commitment phase by column (rank r commits the block zkfhe_shard_range gives it; one ncclAllGather of
+ *     64 bytes per column);
+ *   - the quotient by expression: rank r owns a block of the gate groups, permutation chunks and lookups, transforms
+ *     (lagrange -> coeff -> extended coset) only the columns those expressions read, evaluates them on the whole
+ *     extended domain and contributes 4n x 32 bytes to one ncclAllGather, after which every rank sums the shares;
+ *   - the openings by column: rank r evaluates at x, and adds into the SHPLONK sums, the polynomials it already holds
+ *     in coefficient form (two more all-gathers: ~900 / ranks scalars, 6n x 32 bytes).
+ * Witness generation, lookup permutations, grand products and the transcript are replicated.  Shares are combined by
+ * field additions in rank order on every rank, so every rank returns the same proof, byte-identical to the
+ * single-GPU proof.  libnccl.so.2 is loaded with dlopen on first use.  Any rank count works. */
 int zkfhe_comm_unique_id(uint8_t* out128);                 /* ncclGetUniqueId: call on one rank, hand the bytes to all */
 int zkfhe_comm_init(zkfhe_ctx* ctx, int rank, int n_ranks, const uint8_t* id128);   /* collective: ncclCommInitRank */
 int zkfhe_comm_destroy(zkfhe_ctx* ctx);

@@ -307,11 +307,11 @@ def test_small_circuit_end_to_end_both_transcripts(transcript):
 
 
 # ---- one proof sharded over several (here: virtual) ranks ------------------------------------------------------
-@pytest.mark.parametrize("G", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("G", [2, 3, 4, 5, 8, 13])
 def test_sharded_proof_is_byte_identical_small_circuit(G):
-    """Column-sharded commitment phases and the coset-sharded quotient (zkfhe_set_virtual_ranks: all G shards computed
-    on this GPU, no collective) must give the single-GPU proof byte for byte -- every rank count, incl. the ones where a
-    shard takes several cosets (G < 4) or the shards of a coset split the expression list (G > 4)."""
+    """Column-sharded commitment phases, the expression-sharded quotient and the column-sharded openings
+    (zkfhe_set_virtual_ranks: all G shards computed on this GPU, no collective) must give the single-GPU proof byte
+    for byte -- every rank count, incl. ones that do not divide the column / chunk / lookup counts."""
     import zk_fhe_b200
     from zk_fhe_b200 import bfv, prover
     ctx = zk_fhe_b200.Context(0)

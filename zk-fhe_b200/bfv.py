@@ -20,9 +20,14 @@ class BfvParams:
     Q: int = 536870909
     T: int = 7
     B: int = 19
+    # RNS: one circuit per limb prime q_i proves c0 = pk0*u + delta_i*m + e0 (mod q_i) with delta_i = (Q_total // T) mod q_i,
+    # Q_total the product of the limb primes (the reference has a single modulus and delta = Q // T, bfv.rs:112)
+    delta_override: int = None
 
     @property
     def delta(self):
+        if self.delta_override is not None:
+            return self.delta_override
         return self.Q // self.T        # bfv.rs:112
 
 

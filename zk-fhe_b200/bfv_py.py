@@ -22,6 +22,25 @@ from .bfv import INPUT_KEYS, BfvParams
 from .poly import Poly
 
 
+def encrypt_with(ctx, params, values):
+    """c0, c1 for GIVEN pk0, pk1, u, e0, e1, m (ints in [0, Q)) with the library's Poly arithmetic; returns the bfv.in dict.
+    `params.delta` is the scaling factor (Q // T, or an RNS limb's (Q_total // T) mod q_i)."""
+    N, Q = params.N, params.Q
+    cyclo = [1] + [0] * (N - 1) + [1]
+    pc = Poly.from_string(ctx, [str(x) for x in cyclo], Q)
+
+    def ring_mul(a, b):
+        pa, pb = Poly.from_string(ctx, [str(x) for x in a], Q), Poly.from_string(ctx, [str(x) for x in b], Q)
+        _, rem = pa.mul(pb).reduce_by_modulus(Q).divide_by_cyclo(pc, Q)
+        return rem.coefficients[-N:]
+
+    delta = params.delta
+    c0 = [(r + delta * mi + ei) % Q for r, mi, ei in zip(ring_mul(values["pk0"], values["u"]), values["m"], values["e0"])]
+    c1 = [(r + ei) % Q for r, ei in zip(ring_mul(values["pk1"], values["u"]), values["e1"])]
+    d = dict(values, c0=c0, c1=c1, cyclo=cyclo)
+    return {k: [str(x) for x in d[k]] for k in INPUT_KEYS}
+
+
 def keygen_and_encrypt(ctx, params=BfvParams(), rng=None, with_secret_key=True):
     """One synthetic (public key, message, randomness, ciphertext) tuple as a bfv.in dict.
 
@@ -60,7 +79,7 @@ def keygen_and_encrypt(ctx, params=BfvParams(), rng=None, with_secret_key=True):
         pk0, pk1 = uniform(), uniform()
     u, e0, e1 = ternary(), error(), error()
     m = [int(x) % Q for x in rng.integers(-(T // 2), T // 2 + 1, N)]
-    delta = Q // T
+    delta = params.delta                       # Q // T, or the RNS limb's (Q_total // T) mod q_i
     c0 = [(r + delta * mi + ei) % Q for r, mi, ei in zip(ring_mul(pk0, u), m, e0)]
     c1 = [(r + ei) % Q for r, ei in zip(ring_mul(pk1, u), e1)]
     d = dict(pk0=pk0, pk1=pk1, m=m, u=u, e0=e0, e1=e1, c0=c0, c1=c1, cyclo=cyclo)

@@ -2,8 +2,10 @@
 // the sharded prover uses (an in-place all-gather on the context's stream).
 //
 // The reference has no distributed code at all; this is the B200 side of SURVEY.md section 8(e):
-// commitment phases shard by column, the quotient by coset of the extended domain, and what crosses NVLink is the
-// 64-byte commitments of a phase and the n x 32-byte quotient evaluations of a coset.  Curve points cannot be summed by
+// commitment phases shard by column, the quotient by expression (each rank transforms and evaluates only the columns
+// its block of gates / permutation chunks / lookups reads), the openings by column, and what crosses NVLink is the
+// 64-byte commitments of a phase, one 4n x 32-byte share of the quotient numerator, ~900 evaluations and six n x 32-byte
+// opening sums per rank.  Curve points cannot be summed by
 // ncclAllReduce, and gathering (never reducing) keeps every rank's transcript -- hence the proof -- byte-identical to
 // the single-GPU one.
 //

@@ -19,9 +19,11 @@
 //   4  W h_0, h_1, h_2 (quotient pieces)       C x
 //   5  W evaluations at x * w^rot (order = opening table)
 //   6  SHPLONK: C y', C v, W [h'], C u, W [L/(X-u)]
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <new>
+#include <nvtx3/nvToolsExt.h>
 #include "prover.cuh"
 #include "witness.cuh"
 #include "witness_types.cuh"
@@ -363,41 +365,33 @@ __global__ void k_quotient_lookup(const QArgs q, uint32_t part_base) {
     acc = add(acc, mul(mul(l_act, mul(d, sub(ap, ap_m1))), fe_load(q.ypow + (q.NE - 5 - Bl))));
     fe_store(q.part + (uint64_t)(part_base + blockIdx.y) * q.n4 + row, acc);
 }
-// h_ext[row] = (sum_g part[g][row]) / (X^n - 1); X^n - 1 takes 4 values on the extended coset
-__global__ void k_quotient_finish(const fr_t* part, uint32_t groups, uint32_t n4, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
+// Sharded quotient: every shard evaluates ITS expressions (a block of the gate groups, of the
+// permutation chunks and of the lookups) on the whole extended coset, from the extended form of the columns those
+// expressions read -- and of those only.
+// out[row] = sum_g part[g][row]: one shard's share of the numerator
+__global__ void k_quotient_partial_sum(const fr_t* part, uint32_t groups, uint32_t rows, fr_t* out) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n4) return;
+    if (row >= rows) return;
     fr_t acc = fe_zero<FR>();
-    for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * n4 + row));
-    const uint32_t r = row & 3;
-    fe_store(h_ext + row, mul(acc, r == 0 ? zh0 : r == 1 ? zh1 : r == 2 ? zh2 : zh3));
-}
-
-// Sharded quotient (one coset of H per shard):
-// out[c][i] = in[c][i] * g^i  -- the coset shift in front of a plain n-point NTT, E_coset[i] = P(g * w^i), g = zeta * w_ext^coset
-__global__ void k_shift_scale(const fr_t* in, uint64_t in_stride, fr_t* out, uint64_t out_stride, const fr_t* gpow, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-    if (i >= n) return;
-    fe_store(out + (uint64_t)c * out_stride + i, mul(fe_load(in + (uint64_t)c * in_stride + i), fe_load(gpow + i)));
-}
-// out[row] = sum_g part[g][row]: one shard's share of the numerator on its coset
-__global__ void k_quotient_partial_sum(const fr_t* part, uint32_t groups, uint32_t n, fr_t* out) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    fr_t acc = fe_zero<FR>();
-    for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * n + row));
+    for (uint32_t g = 0; g < groups; g++) acc = add(acc, fe_load(part + (uint64_t)g * rows + row));
     fe_store(out + row, acc);
 }
-// h_ext[4 i + c] = zh[c] * sum over the shards v that worked on coset c of gathered[v][i]
-struct ShardMap { uint32_t G; uint8_t coset[64]; };
-__global__ void k_quotient_assemble(const fr_t* gathered, ShardMap m, uint32_t n, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
+// h_ext[e] = (sum over the shards of gathered[v][e]) / (X^n - 1); X^n - 1 takes 4 values on the extended coset
+__global__ void k_quotient_assemble(const fr_t* gathered, uint32_t G, uint32_t n4, fr_t zh0, fr_t zh1, fr_t zh2, fr_t zh3, fr_t* h_ext) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (n << EXT_SHIFT)) return;
-    const uint32_t c = e & ((1u << EXT_SHIFT) - 1), i = e >> EXT_SHIFT;
-    fr_t acc = fe_zero<FR>();
-    for (uint32_t v = 0; v < m.G; v++)
-        if (m.coset[v] == c) acc = add(acc, fe_load(gathered + (uint64_t)v * n + i));
-    fe_store(h_ext + e, mul(acc, c == 0 ? zh0 : c == 1 ? zh1 : c == 2 ? zh2 : zh3));
+    if (e >= n4) return;
+    fr_t acc = fe_load(gathered + e);
+    for (uint32_t v = 1; v < G; v++) acc = add(acc, fe_load(gathered + (uint64_t)v * n4 + e));
+    const uint32_t r = e & 3;
+    fe_store(h_ext + e, mul(acc, r == 0 ? zh0 : r == 1 ? zh1 : r == 2 ? zh2 : zh3));
+}
+// out[i] = sum over the shards of gathered[v][i] (the f_s of the opening argument, summed from per-shard partial sums)
+__global__ void k_sum_shards(const fr_t* gathered, uint32_t G, uint64_t len, fr_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    fr_t acc = fe_load(gathered + i);
+    for (uint32_t v = 1; v < G; v++) acc = add(acc, fe_load(gathered + (uint64_t)v * len + i));
+    fe_store(out + i, acc);
 }
 
 // ---- evaluations and linear combinations ----------------------------------------------------------
@@ -503,19 +497,31 @@ struct zkfhe_prover {
     int stage = 0;
     uint32_t C_all = 0, ap_base = 0, zp_base = 0, zl_base = 0, r_col = 0, lookup_adv_base = 0;
     fr_t *P = nullptr, *E = nullptr, *inst = nullptr, *inst_ext = nullptr, *blind = nullptr, *misc = nullptr;
-    fr_t* gpow = nullptr;        // [4][n] powers of the coset shifts zeta * w_ext^c (sharded quotient only; built on first use)
-    bool gpow_ready[1u << zkfhe::EXT_SHIFT] = {false, false, false, false};
+    // per proof: which columns of P are already in coefficient form / have their extended form in E (a shard only
+    // transforms the columns its own expressions and openings read; index C_all stands for the instance column)
+    std::vector<uint8_t> coeff_done, ext_done;
     Fr gamma_rlc, theta, beta, gamma, y, x;
     // host wall-clock at the end of each round (every round ends with a synchronising commitment
     // read-back, so these are true round latencies): [0] phase-0 commit, [1] phase-1 advice,
     // [2] lookup permutations, [3] grand products, [4] quotient, [5] evaluations, [6] h' commit, [7] end
     double round_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::chrono::steady_clock::time_point t_mark;
-    void mark_start() { t_mark = std::chrono::steady_clock::now(); }
+    // every round is also an NVTX range (visible in nsys / ncu --nvtx; free when no tool is attached)
+    void mark_start(int first) {
+        t_mark = std::chrono::steady_clock::now();
+        nvtxRangePushA(round_name(first));
+    }
     void mark(int i) {
         auto now = std::chrono::steady_clock::now();
         round_ms[i] = std::chrono::duration<double, std::milli>(now - t_mark).count();
         t_mark = now;
+        nvtxRangePop();
+        if (i >= 1 && i < 7) nvtxRangePushA(round_name(i + 1));
+    }
+    static const char* round_name(int i) {
+        static const char* names[8] = {"zkfhe: phase-0 commit", "zkfhe: phase-1 commit", "zkfhe: lookup permutations", "zkfhe: grand products",
+                                       "zkfhe: quotient", "zkfhe: evaluations", "zkfhe: SHPLONK quotient", "zkfhe: SHPLONK opening"};
+        return names[i];
     }
     zkfhe_prover(const uint8_t seed[32], int kind) : tr(kind) { memcpy(rng_key.k, seed, 32); }
 };
@@ -524,16 +530,69 @@ namespace zkfhe {
 
 static inline fr_t dev(const Fr& a) { fr_t r; memcpy(r.v, a.l, 32); return r; }
 
-// powers g^i, i < n, of the shift of coset c of the extended domain (g = zeta * w_ext^c), cached in the prover
-static int pr_coset_powers(zkfhe_prover* pr, uint32_t c) {
-    zkfhe_ctx* ctx = pr->ctx;
-    const uint32_t n = pr->pk->n;
-    if (!pr->gpow) ZK_CUDA(ctx, cudaMalloc(&pr->gpow, ((size_t)n << EXT_SHIFT) * 32));
-    if (pr->gpow_ready[c]) return ZKFHE_OK;
-    const Fr g = host::mul(host::to_mont(host::FR_ZETA_CANON), host::pow_u64(host::omega(pr->pk->k + EXT_SHIFT), c));
-    k_powers<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pr->gpow + (size_t)c * n, dev(g), n);
-    ZK_CHECK_LAUNCH(ctx);
-    pr->gpow_ready[c] = true;
+// ---- sharding of the quotient and opening rounds ---------------------------------------------------------------
+struct ColRange { uint32_t lo, hi; };
+struct ShardPlan {
+    uint32_t glo, ghi, plo, phi, llo, lhi;     // gate groups, permutation chunks, lookups of this shard
+    std::vector<ColRange> cols;                // columns of P whose extended form the shard's expressions read (merged, sorted)
+    bool inst;                                 // ... and the instance column
+};
+static void merge_ranges(std::vector<ColRange>& r) {
+    std::vector<ColRange> in;
+    for (auto& x : r) if (x.hi > x.lo) in.push_back(x);
+    std::sort(in.begin(), in.end(), [](const ColRange& a, const ColRange& b) { return a.lo < b.lo; });
+    r.clear();
+    for (auto& x : in) {
+        if (!r.empty() && x.lo <= r.back().hi) r.back().hi = std::max(r.back().hi, x.hi);
+        else r.push_back(x);
+    }
+}
+static ShardPlan shard_plan(const zkfhe_prover* pr, uint32_t G, uint32_t v, uint32_t g_gate, uint32_t cols_per_group) {
+    const zkfhe_pk* pk = pr->pk;
+    ShardPlan sp{};
+    shard_range(g_gate, G, v, &sp.glo, &sp.ghi);
+    shard_range(pk->n_chunks, G, v, &sp.plo, &sp.phi);
+    shard_range(pk->n_lookup, G, v, &sp.llo, &sp.lhi);
+    const uint32_t n_gr = pk->n_gate0 + pk->n_gate1 + pk->n_rlc;
+    sp.cols.push_back({sp.glo * cols_per_group, std::min(sp.ghi * cols_per_group, n_gr)});               // gate / RLC columns
+    sp.cols.push_back({std::min(sp.plo * PERM_CHUNK, pk->n_advice), std::min(sp.phi * PERM_CHUNK, pk->n_advice)});   // permuted advice columns
+    if (sp.phi > sp.plo) sp.cols.push_back({pr->zp_base + (sp.plo ? sp.plo - 1 : 0), pr->zp_base + sp.phi});         // Z_j and Z_{j-1}
+    sp.cols.push_back({pr->lookup_adv_base + sp.llo, pr->lookup_adv_base + sp.lhi});
+    sp.cols.push_back({pr->ap_base + 2 * sp.llo, pr->ap_base + 2 * sp.lhi});
+    sp.cols.push_back({pr->zl_base + sp.llo, pr->zl_base + sp.lhi});
+    merge_ranges(sp.cols);
+    sp.inst = sp.phi * PERM_CHUNK > pk->n_advice + 1 && sp.plo * PERM_CHUNK <= pk->n_advice + 1;         // permutation column n_advice + 1
+    return sp;
+}
+// coefficient form (in place in P) of columns [lo, hi) that are still in Lagrange form
+static int ensure_coeff(zkfhe_prover* pr, uint32_t lo, uint32_t hi) {
+    const uint32_t n = pr->pk->n, k = pr->pk->k;
+    for (uint32_t c = lo; c < hi;) {
+        if (pr->coeff_done[c]) { c++; continue; }
+        uint32_t e = c;
+        while (e < hi && !pr->coeff_done[e]) pr->coeff_done[e++] = 1;
+        ZK_TRY(ntt_run(pr->ctx, pr->P + (size_t)c * n, n, n, pr->P + (size_t)c * n, n, k, e - c, 1, 0));
+        c = e;
+    }
+    return ZKFHE_OK;
+}
+// extended form (P -> E) of columns [lo, hi) that do not have it yet
+static int ensure_ext(zkfhe_prover* pr, uint32_t lo, uint32_t hi) {
+    const uint32_t n = pr->pk->n, n4 = n << EXT_SHIFT, k4 = pr->pk->k + EXT_SHIFT;
+    ZK_TRY(ensure_coeff(pr, lo, hi));
+    for (uint32_t c = lo; c < hi;) {
+        if (pr->ext_done[c]) { c++; continue; }
+        uint32_t e = c;
+        while (e < hi && !pr->ext_done[e]) pr->ext_done[e++] = 1;
+        ZK_TRY(ntt_run(pr->ctx, pr->P + (size_t)c * n, n, n, pr->E + (size_t)c * n4, n4, k4, e - c, 0, 1));
+        c = e;
+    }
+    return ZKFHE_OK;
+}
+static int ensure_inst(zkfhe_prover* pr, bool ext) {
+    const uint32_t n = pr->pk->n, n4 = n << EXT_SHIFT, C = pr->C_all;
+    if (!pr->coeff_done[C]) { ZK_TRY(ntt_run(pr->ctx, pr->inst, n, n, pr->inst, n, pr->pk->k, 1, 1, 0)); pr->coeff_done[C] = 1; }
+    if (ext && !pr->ext_done[C]) { ZK_TRY(ntt_run(pr->ctx, pr->inst, n, n, pr->inst_ext, n4, pr->pk->k + EXT_SHIFT, 1, 0, 1)); pr->ext_done[C] = 1; }
     return ZKFHE_OK;
 }
 
@@ -594,7 +653,7 @@ void zkfhe_prover_free(zkfhe_prover* pr) {
     if (!pr) return;
     cudaSetDevice(pr->ctx->device);
     cudaStreamSynchronize(pr->ctx->stream);
-    fr_t* bufs[] = {pr->P, pr->E, pr->inst, pr->inst_ext, pr->blind, pr->misc, pr->gpow};
+    fr_t* bufs[] = {pr->P, pr->E, pr->inst, pr->inst_ext, pr->blind, pr->misc};
     for (auto b : bufs) if (b) cudaFree(b);
     delete pr;
 }
@@ -652,7 +711,7 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     zkfhe_pk* pk = pr->pk;
     if (pr->stage != 0) return fail(ctx, ZKFHE_ERR_STATE, "prove_phase0: called out of order");
     if (w->ctx != ctx) return fail(ctx, ZKFHE_ERR_ARG, "prove_phase0: witness and prover belong to different contexts");
-    pr->mark_start();
+    pr->mark_start(0);
     if (w->adv[0].size != pk->cells[0] || w->make_public.size() != pk->instances)
         return fail(ctx, ZKFHE_ERR_ARG, "prove_phase0: witness shape differs from the proving key (%zu cells, key has %llu)",
                     w->adv[0].size, (unsigned long long)pk->cells[0]);
@@ -692,7 +751,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     zkfhe_pk* pk = pr->pk;
     if (pr->stage != 1) return fail(ctx, ZKFHE_ERR_STATE, "prove_finish: zkfhe_prove_phase0 must run first");
     if (w->ctx != ctx) return fail(ctx, ZKFHE_ERR_ARG, "prove_finish: witness and prover belong to different contexts");
-    pr->mark_start();
+    pr->mark_start(1);
     size_t lookups = 0;
     for (int c = 0; c < 3; c++) lookups += w->lk[c].size;
     if (w->adv[1].size != pk->cells[1] || w->adv[2].size != pk->cells[2] || lookups != pk->lookups || w->lk[1].size != lookups)
@@ -785,12 +844,28 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     pr->mark(3);
 
     // ---- round 4: quotient -----------------------------------------------------------------------------
+    // From here on the work is split into G shards (G = 1 on one GPU): shard v owns a block of the gate groups, of the
+    // permutation chunks and of the lookups, transforms only the columns those expressions read, and later opens the
+    // columns it holds in coefficient form.  Under NCCL a rank computes its own shard and three all-gathers per proof
+    // carry the shares (numerator: 4n x 32 B per rank; evaluations: ~900 / G scalars; opening sums: 6n x 32 B per
+    // rank); in virtual mode (tests) one process computes all shards one after the other.  The sums are field
+    // additions done by every rank in the same order, so every rank's transcript -- and proof -- is identical.
     fr_t* h_ext = pr->misc;                       // [4n]
     fr_t* h_coef = pr->misc + n4;                 // [4n] -> pieces h_0..h_2 in the first 3n
+    const Shards sh = shards_of(ctx);
+    const uint32_t cols_per_group = 16;
+    const uint32_t g_gate = (n_gate + pk->n_rlc + cols_per_group - 1) / cols_per_group;
+    std::vector<ShardPlan> plans;
+    for (uint32_t v = 0; v < sh.G; v++) plans.push_back(shard_plan(pr, sh.G, v, g_gate, cols_per_group));
+    // who opens which column of P: the first shard that needs its coefficient form anyway; shard 0 for the rest
+    std::vector<uint32_t> owner(pr->C_all, 0xffffffffu);
+    for (uint32_t v = 0; v < sh.G; v++)
+        for (auto& r : plans[v].cols)
+            for (uint32_t c = r.lo; c < r.hi; c++) if (owner[c] == 0xffffffffu) owner[c] = v;
+    for (auto& o : owner) if (o == 0xffffffffu) o = 0;
+    pr->coeff_done.assign(pr->C_all + 1, 0);
+    pr->ext_done.assign(pr->C_all + 1, 0);
     {
-        // coefficient form of everything (Lagrange values are no longer needed)
-        ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->P, n, k, pr->C_all, 1, 0));
-        ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst, n, k, 1, 1, 0));
         const uint32_t NE = n_gate + pk->n_rlc + 2 * pk->n_chunks + 1 + 5 * pk->n_lookup;
         std::vector<Fr> ypow(NE);
         ypow[0] = host::FR_ONE;
@@ -799,92 +874,39 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_CUDA(ctx, cudaMemcpyAsync(d_ypow, ypow.data(), (size_t)NE * 32, cudaMemcpyHostToDevice, ctx->stream));
         QArgs q{};
         q.E = pr->E; q.F = pk->fixed_ext; q.inst_ext = pr->inst_ext; q.tw_ext = dom4->tw_fwd; q.ypow = d_ypow;
-        q.delta_pow = pk->delta_pow; q.f_stride = n4;
+        q.delta_pow = pk->delta_pow; q.f_stride = n4; q.n4 = n4; q.rot = 1u << EXT_SHIFT; q.f_rs = 1; q.f_ro = 0;
         q.n_gate = n_gate; q.n_rlc = pk->n_rlc; q.rlc_base = n_gate; q.n_advice = pk->n_advice; q.n_lookup = pk->n_lookup;
         q.n_chunks = pk->n_chunks; q.n_perm = pk->n_perm; q.NE = NE; q.zp_base = pr->zp_base; q.zl_base = pr->zl_base;
         q.ap_base = pr->ap_base; q.lookup_adv_base = pr->lookup_adv_base; q.usable = usable;
         q.fx_qgate = pk->fx_qgate; q.fx_qrlc = pk->fx_qrlc; q.fx_const = pk->fx_const; q.fx_table = pk->fx_table;
         q.fx_l0 = pk->fx_l0; q.fx_sigma = pk->fx_sigma;
-        q.cols_per_group = 16;
+        q.cols_per_group = cols_per_group;
         q.gamma_rlc = dev(pr->gamma_rlc); q.beta = dev(pr->beta); q.gamma = dev(pr->gamma);
         q.zeta = dev(host::to_mont(host::FR_ZETA_CANON));
-        const uint32_t g_gate = (n_gate + pk->n_rlc + q.cols_per_group - 1) / q.cols_per_group;
         // 1 / (X^n - 1) on zeta * w_ext^j: X^n = zeta^n * (w_ext^n)^j, w_ext^n is a primitive 4th root of unity
         Fr zeta = host::to_mont(host::FR_ZETA_CANON), zn = host::pow_u64(zeta, n), i4 = host::pow_u64(host::omega(k4), n);
         Fr zh[4], cur = zn;
         for (int r = 0; r < 4; r++) { zh[r] = host::inv(host::sub(cur, host::FR_ONE)); cur = host::mul(cur, i4); }
-        const Shards sh = shards_of(ctx);
-        if (sh.G == 1) {
-            // one GPU: the whole extended coset zeta * H_ext at once
-            ZK_TRY(ntt_run(ctx, pr->P, n, n, pr->E, n4, k4, pr->C_all, 0, 1));
-            ZK_TRY(ntt_run(ctx, pr->inst, n, n, pr->inst_ext, n4, k4, 1, 0, 1));
-            q.n4 = n4; q.rot = 1u << EXT_SHIFT; q.f_rs = 1; q.f_ro = 0;
-            const uint32_t groups = g_gate + pk->n_chunks + pk->n_lookup;
+        fr_t* gathered;      // [G][4n]: every shard's share of the numerator
+        ZK_TRY(ws_get(ctx, "pr_qgather", (size_t)sh.G * n4 * 32, (void**)&gathered));
+        const uint32_t bx = (n4 + 127) / 128;
+        for (uint32_t v = sh.first; v < sh.last; v++) {
+            const ShardPlan& sp = plans[v];
+            for (auto& r : sp.cols) ZK_TRY(ensure_ext(pr, r.lo, r.hi));
+            if (sp.inst) ZK_TRY(ensure_inst(pr, true));
+            const uint32_t groups = (sp.ghi - sp.glo) + (sp.phi - sp.plo) + (sp.lhi - sp.llo);
             fr_t* part;
-            ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)groups * n4 * 32, (void**)&part));
-            q.part = part;
-            const uint32_t bx = (n4 + 127) / 128;
-            k_quotient_gates<<<dim3(bx, g_gate), 128, 0, ctx->stream>>>(q);
-            ZK_CHECK_LAUNCH(ctx);
-            k_quotient_perm<<<dim3(bx, pk->n_chunks), 128, 0, ctx->stream>>>(q, g_gate);
-            ZK_CHECK_LAUNCH(ctx);
-            if (pk->n_lookup) {
-                k_quotient_lookup<<<dim3(bx, pk->n_lookup), 128, 0, ctx->stream>>>(q, g_gate + pk->n_chunks);
-                ZK_CHECK_LAUNCH(ctx);
-            }
-            k_quotient_finish<<<bx, 128, 0, ctx->stream>>>(part, groups, n4, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
-            ZK_CHECK_LAUNCH(ctx);
-        } else {
-            // several GPUs: zeta * H_ext is the union of the four cosets g_c * H, g_c = zeta * w_ext^c (extended index
-            // 4 i + c), and rotations stay inside a coset.  Shard v works on coset v mod 4; when more than four shards
-            // exist, the shards of one coset split the expression list (gate groups, permutation chunks, lookups)
-            // between them.  Each shard leaves n partial numerator values; one all-gather; every rank then sums the
-            // shares of each coset, divides by X^n - 1 and interleaves.
-            const uint32_t NC = 1u << EXT_SHIFT;
-            // work slots: slot s is coset s mod 4; with more than four shards the slots of one coset split the
-            // expression list between them.  Shard v owns slots v, v + G, ... (exactly slot v once G >= 4).
-            const uint32_t S = sh.G < NC ? NC : sh.G;
-            ShardMap map{};
-            map.G = S;
-            uint32_t halves[1u << EXT_SHIFT] = {0, 0, 0, 0}, half_of[64];
-            for (uint32_t t = 0; t < S; t++) { map.coset[t] = (uint8_t)(t % NC); half_of[t] = halves[t % NC]++; }
-            fr_t* gathered;      // [S][n]
-            ZK_TRY(ws_get(ctx, "pr_qgather", (size_t)S * n * 32, (void**)&gathered));
-            const uint32_t bx = (n + 127) / 128;
-            for (uint32_t v = sh.first; v < sh.last; v++)
-                for (uint32_t t = v; t < S; t += sh.G) {
-                    const uint32_t c = map.coset[t], H = halves[c], hidx = half_of[t];
-                    ZK_TRY(pr_coset_powers(pr, c));
-                    const fr_t* gpow = pr->gpow + (size_t)c * n;
-                    k_shift_scale<<<dim3((n + 255) / 256, pr->C_all), 256, 0, ctx->stream>>>(pr->P, n, pr->E, n, gpow, n);
-                    ZK_CHECK_LAUNCH(ctx);
-                    k_shift_scale<<<dim3((n + 255) / 256, 1), 256, 0, ctx->stream>>>(pr->inst, n, pr->inst_ext, n, gpow, n);
-                    ZK_CHECK_LAUNCH(ctx);
-                    ZK_TRY(ntt_run(ctx, pr->E, n, n, pr->E, n, k, pr->C_all, 0, 0));
-                    ZK_TRY(ntt_run(ctx, pr->inst_ext, n, n, pr->inst_ext, n, k, 1, 0, 0));
-                    q.n4 = n; q.rot = 1; q.f_rs = NC; q.f_ro = c;
-                    uint32_t glo, ghi, plo, phi, llo, lhi;
-                    shard_range(g_gate, H, hidx, &glo, &ghi);
-                    shard_range(pk->n_chunks, H, hidx, &plo, &phi);
-                    shard_range(pk->n_lookup, H, hidx, &llo, &lhi);
-                    const uint32_t groups = (ghi - glo) + (phi - plo) + (lhi - llo);
-                    fr_t* part;
-                    ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)(groups + 1) * n * 32, (void**)&part));
-                    q.part = part; q.grp_base = glo; q.perm_base = plo; q.lookup_base = llo;
-                    if (ghi > glo) { k_quotient_gates<<<dim3(bx, ghi - glo), 128, 0, ctx->stream>>>(q); ZK_CHECK_LAUNCH(ctx); }
-                    if (phi > plo) { k_quotient_perm<<<dim3(bx, phi - plo), 128, 0, ctx->stream>>>(q, ghi - glo); ZK_CHECK_LAUNCH(ctx); }
-                    if (lhi > llo) { k_quotient_lookup<<<dim3(bx, lhi - llo), 128, 0, ctx->stream>>>(q, (ghi - glo) + (phi - plo)); ZK_CHECK_LAUNCH(ctx); }
-                    k_quotient_partial_sum<<<bx, 128, 0, ctx->stream>>>(part, groups, n, gathered + (size_t)t * n);
-                    ZK_CHECK_LAUNCH(ctx);
-                }
-            if (ctx->nccl_comm)
-                for (uint32_t base = 0; base < S; base += sh.G) {        // one all-gather per round of slots (one in all when G >= 4)
-                    if (base + sh.G > S) return fail(ctx, ZKFHE_ERR_ARG, "prove: %u ranks do not divide the %u cosets of the extended domain", sh.G, NC);
-                    ZK_TRY(comm_allgather(ctx, gathered + (size_t)base * n, (size_t)n * 32));
-                }
-            k_quotient_assemble<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(gathered, map, n, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
+            ZK_TRY(ws_get(ctx, "pr_qpart", (size_t)(groups + 1) * n4 * 32, (void**)&part));
+            q.part = part; q.grp_base = sp.glo; q.perm_base = sp.plo; q.lookup_base = sp.llo;
+            if (sp.ghi > sp.glo) { k_quotient_gates<<<dim3(bx, sp.ghi - sp.glo), 128, 0, ctx->stream>>>(q); ZK_CHECK_LAUNCH(ctx); }
+            if (sp.phi > sp.plo) { k_quotient_perm<<<dim3(bx, sp.phi - sp.plo), 128, 0, ctx->stream>>>(q, sp.ghi - sp.glo); ZK_CHECK_LAUNCH(ctx); }
+            if (sp.lhi > sp.llo) { k_quotient_lookup<<<dim3(bx, sp.lhi - sp.llo), 128, 0, ctx->stream>>>(q, (sp.ghi - sp.glo) + (sp.phi - sp.plo)); ZK_CHECK_LAUNCH(ctx); }
+            k_quotient_partial_sum<<<bx, 128, 0, ctx->stream>>>(part, groups, n4, gathered + (size_t)v * n4);
             ZK_CHECK_LAUNCH(ctx);
         }
+        ZK_TRY(comm_allgather(ctx, gathered, (size_t)n4 * 32));
+        k_quotient_assemble<<<bx, 128, 0, ctx->stream>>>(gathered, sh.G, n4, dev(zh[0]), dev(zh[1]), dev(zh[2]), dev(zh[3]), h_ext);
+        ZK_CHECK_LAUNCH(ctx);
         ZK_CUDA(ctx, cudaMemcpyAsync(h_coef, h_ext, (size_t)n4 * 32, cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_TRY(ntt_run(ctx, h_coef, n4, n4, h_coef, n4, k4, 1, 1, 1));
         ZK_TRY(commit_and_write(pr, h_coef, 3, 0));
@@ -893,29 +915,38 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
     pr->mark(4);
 
     // ---- opening table -----------------------------------------------------------------------------------
-    struct Opened { const fr_t* coef; int set; };
+    // `own`: the shard that evaluates / sums the polynomial (columns of P: whoever transformed them; fixed
+    // polynomials, resident in coefficient form on every rank: even blocks; h_comb: shard 0)
+    struct Opened { const fr_t* coef; int set; uint32_t own; };
     std::vector<Opened> polys;
-    for (uint32_t c = 0; c < pk->n_advice; c++)
-        polys.push_back({pr->P + (size_t)c * n, c < n_gate ? SET_0123 : c < n_gate + pk->n_rlc ? SET_012 : SET_0});
-    for (uint32_t f = 0; f < pk->n_fixed; f++) {
-        if (f >= pk->fx_l0 && f < pk->fx_sigma) continue;         // l_0, l_last, l_active: evaluated by the verifier
-        polys.push_back({pk->fixed_coeff + (size_t)f * n, SET_0});
+    auto pcol = [&](uint32_t c, int set) { polys.push_back({pr->P + (size_t)c * n, set, owner[c]}); };
+    for (uint32_t c = 0; c < pk->n_advice; c++) pcol(c, c < n_gate ? SET_0123 : c < n_gate + pk->n_rlc ? SET_012 : SET_0);
+    {
+        const uint32_t n_open_fixed = pk->n_fixed - (pk->fx_sigma - pk->fx_l0), per = shard_per(n_open_fixed, sh.G);
+        uint32_t idx = 0;
+        for (uint32_t f = 0; f < pk->n_fixed; f++) {
+            if (f >= pk->fx_l0 && f < pk->fx_sigma) continue;         // l_0, l_last, l_active: evaluated by the verifier
+            polys.push_back({pk->fixed_coeff + (size_t)f * n, SET_0, idx++ / per});
+        }
     }
     for (uint32_t l = 0; l < pk->n_lookup; l++) {
-        polys.push_back({pr->P + (size_t)(pr->ap_base + 2 * l) * n, SET_0m1});
-        polys.push_back({pr->P + (size_t)(pr->ap_base + 2 * l + 1) * n, SET_0});
-        polys.push_back({pr->P + (size_t)(pr->zl_base + l) * n, SET_01});
+        pcol(pr->ap_base + 2 * l, SET_0m1);
+        pcol(pr->ap_base + 2 * l + 1, SET_0);
+        pcol(pr->zl_base + l, SET_01);
     }
-    for (uint32_t j = 0; j < pk->n_chunks; j++)
-        polys.push_back({pr->P + (size_t)(pr->zp_base + j) * n, j + 1 < pk->n_chunks ? SET_01L : SET_01});
-    polys.push_back({pr->P + (size_t)pr->r_col * n, SET_0});
+    for (uint32_t j = 0; j < pk->n_chunks; j++) pcol(pr->zp_base + j, j + 1 < pk->n_chunks ? SET_01L : SET_01);
+    pcol(pr->r_col, SET_0);
     fr_t* h_comb = pr->misc + 3 * (size_t)n4;                      // [n]
     {
         Fr xn = host::pow_u64(pr->x, n);
         k_axpy3<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h_coef, n, dev(xn), dev(host::sqr(xn)), h_comb);
         ZK_CHECK_LAUNCH(ctx);
     }
-    polys.push_back({h_comb, SET_0});
+    polys.push_back({h_comb, SET_0, 0});
+    // every column a shard opens must be in coefficient form there (columns no expression reads, e.g. R, were not yet)
+    for (uint32_t v = sh.first; v < sh.last; v++)
+        for (uint32_t c = 0; c < pr->C_all; c++)
+            if (owner[c] == v) ZK_TRY(ensure_coeff(pr, c, c + 1));
 
     // ---- round 5: evaluations ------------------------------------------------------------------------------
     Fr wk = host::omega(k), winv = host::inv(wk);
@@ -926,20 +957,34 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         k_powers<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pw + (size_t)i * n, dev(pts[i]), n);
         ZK_CHECK_LAUNCH(ctx);
     }
-    std::vector<EvalTask> tasks;
-    for (auto& p : polys)
-        for (int r = 0; r < SET_SIZE[p.set]; r++) tasks.push_back(EvalTask{p.coef, (uint32_t)point_index(SET_ROTS[p.set][r])});
-    std::vector<Fr> evals(tasks.size());
+    size_t n_tasks = 0;
+    for (auto& p : polys) n_tasks += SET_SIZE[p.set];
+    std::vector<Fr> evals(n_tasks);
     {
+        // tasks grouped by shard; slot (v, i) of the gathered array is shard v's i-th task
+        std::vector<std::vector<EvalTask>> tasks(sh.G);
+        for (auto& p : polys)
+            for (int r = 0; r < SET_SIZE[p.set]; r++) tasks[p.own].push_back(EvalTask{p.coef, (uint32_t)point_index(SET_ROTS[p.set][r])});
+        size_t max_t = 1;
+        for (auto& t : tasks) max_t = std::max(max_t, t.size());
         EvalTask* d_tasks;
-        fr_t* d_out;
-        ZK_TRY(ws_get(ctx, "pr_tasks", tasks.size() * sizeof(EvalTask), (void**)&d_tasks));
-        ZK_TRY(ws_get(ctx, "pr_evals", tasks.size() * 32, (void**)&d_out));
-        ZK_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(EvalTask), cudaMemcpyHostToDevice, ctx->stream));
-        k_eval<<<(uint32_t)tasks.size(), 256, 0, ctx->stream>>>(d_tasks, pw, n, d_out);
-        ZK_CHECK_LAUNCH(ctx);
-        ZK_CUDA(ctx, cudaMemcpyAsync(evals.data(), d_out, tasks.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        fr_t* d_out;      // [G][max_t]
+        ZK_TRY(ws_get(ctx, "pr_tasks", max_t * sizeof(EvalTask), (void**)&d_tasks));
+        ZK_TRY(ws_get(ctx, "pr_evals", sh.G * max_t * 32, (void**)&d_out));
+        for (uint32_t v = sh.first; v < sh.last; v++) {
+            if (tasks[v].empty()) continue;
+            ZK_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks[v].data(), tasks[v].size() * sizeof(EvalTask), cudaMemcpyHostToDevice, ctx->stream));
+            k_eval<<<(uint32_t)tasks[v].size(), 256, 0, ctx->stream>>>(d_tasks, pw, n, d_out + (size_t)v * max_t);
+            ZK_CHECK_LAUNCH(ctx);
+        }
+        ZK_TRY(comm_allgather(ctx, d_out, max_t * 32));
+        std::vector<Fr> flat(sh.G * max_t);
+        ZK_CUDA(ctx, cudaMemcpyAsync(flat.data(), d_out, flat.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
         ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<size_t> next(sh.G, 0);
+        size_t ei = 0;
+        for (auto& p : polys)
+            for (int r = 0; r < SET_SIZE[p.set]; r++) evals[ei++] = flat[(size_t)p.own * max_t + next[p.own]++];
     }
     // h_comb(x) is implied by the other evaluations (the verifier recomputes it): not written
     for (size_t i = 0; i + 1 < evals.size(); i++) pr->tr.write_scalar(evals[i]);
@@ -949,9 +994,11 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         pr->mark(5);
         Fr yq = pr->tr.squeeze();
         Fr v = pr->tr.squeeze();
-        // per set: polynomial list, combined evaluations e_t = sum_j yq^j eval_j(t)
-        std::vector<const fr_t*> set_polys[6];
-        std::vector<Fr> set_coef[6];
+        // per set: polynomial list (split by shard), combined evaluations e_t = sum_j yq^j eval_j(t)
+        std::vector<std::vector<const fr_t*>> set_polys[6];
+        std::vector<std::vector<Fr>> set_coef[6];
+        size_t set_count[6] = {0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < 6; s++) { set_polys[s].resize(sh.G); set_coef[s].resize(sh.G); }
         Fr set_eval[6][4];
         for (int s = 0; s < 6; s++) for (int r = 0; r < 4; r++) set_eval[s][r] = host::FR_ZERO;
         Fr ypow_set[6];
@@ -959,8 +1006,9 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         size_t ei = 0;
         for (auto& p : polys) {
             const int s = p.set;
-            set_polys[s].push_back(p.coef);
-            set_coef[s].push_back(ypow_set[s]);
+            set_polys[s][p.own].push_back(p.coef);
+            set_coef[s][p.own].push_back(ypow_set[s]);
+            set_count[s]++;
             for (int r = 0; r < SET_SIZE[s]; r++) set_eval[s][r] = host::add(set_eval[s][r], host::mul(ypow_set[s], evals[ei + r]));
             ei += SET_SIZE[s];
             ypow_set[s] = host::mul(ypow_set[s], yq);
@@ -989,10 +1037,10 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         Fr vpow = host::FR_ONE;
         const fr_t** d_ptrs;
         fr_t* d_coef;
-        size_t total_m = 0, set_off[6];
-        for (int s = 0; s < 6; s++) { set_off[s] = total_m; total_m += set_polys[s].size(); }
-        ZK_TRY(ws_get(ctx, "pr_lc_ptrs", (total_m + 8) * 8, (void**)&d_ptrs));
-        ZK_TRY(ws_get(ctx, "pr_lc_coef", (total_m + 8) * 32, (void**)&d_coef));
+        fr_t* fshare;        // [G][6][n]: every shard's share of the six f_s
+        ZK_TRY(ws_get(ctx, "pr_lc_ptrs", (polys.size() + 8) * 8, (void**)&d_ptrs));
+        ZK_TRY(ws_get(ctx, "pr_lc_coef", (polys.size() + 8) * 32, (void**)&d_coef));
+        ZK_TRY(ws_get(ctx, "pr_fshare", (size_t)sh.G * 6 * n * 32, (void**)&fshare));
         ShplonkSets sets{};
         for (int s = 0; s < 6; s++) {
             const int m = SET_SIZE[s];
@@ -1012,18 +1060,27 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
             }
             sets.r[s] = small_from(rcoef[s]);
             sets.z[s] = small_from(zcoef[s]);
-            sets.scale[s] = dev(set_polys[s].empty() ? host::FR_ZERO : vpow);
+            sets.scale[s] = dev(set_count[s] == 0 ? host::FR_ZERO : vpow);
             vpow = host::mul(vpow, v);
-            if (set_polys[s].empty()) {
-                ZK_CUDA(ctx, cudaMemsetAsync(fbuf + (size_t)s * n, 0, (size_t)n * 32, ctx->stream));
-                continue;
-            }
-            ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs + set_off[s], set_polys[s].data(), set_polys[s].size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            ZK_CUDA(ctx, cudaMemcpyAsync(d_coef + set_off[s], set_coef[s].data(), set_coef[s].size() * 32, cudaMemcpyHostToDevice, ctx->stream));
-            k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs + set_off[s], d_coef + set_off[s], (uint32_t)set_polys[s].size(), n,
-                                                                fbuf + (size_t)s * n);
-            ZK_CHECK_LAUNCH(ctx);
         }
+        size_t off = 0;
+        for (uint32_t sv = sh.first; sv < sh.last; sv++)
+            for (int s = 0; s < 6; s++) {
+                fr_t* dst = fshare + ((size_t)sv * 6 + s) * n;
+                const auto& lp = set_polys[s][sv];
+                if (lp.empty()) {
+                    ZK_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)n * 32, ctx->stream));
+                    continue;
+                }
+                ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs + off, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+                ZK_CUDA(ctx, cudaMemcpyAsync(d_coef + off, set_coef[s][sv].data(), lp.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+                k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs + off, d_coef + off, (uint32_t)lp.size(), n, dst);
+                ZK_CHECK_LAUNCH(ctx);
+                off += lp.size();
+            }
+        ZK_TRY(comm_allgather(ctx, fshare, (size_t)6 * n * 32));
+        k_sum_shards<<<(uint32_t)((6 * (size_t)n + 255) / 256), 256, 0, ctx->stream>>>(fshare, sh.G, 6 * (uint64_t)n, fbuf);
+        ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(ntt_run(ctx, fbuf, n, n, fcos, n, k, 6, 0, 1));          // all six f_s on the coset zeta*H
         k_shplonk_quotient<<<(n + 127) / 128, 128, 0, ctx->stream>>>(fcos, sets, dev(zeta), dom->tw_fwd, n, acc);
         ZK_CHECK_LAUNCH(ctx);
@@ -1044,7 +1101,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         Fr cst = host::FR_ZERO;
         vpow = host::FR_ONE;
         for (int s = 0; s < 6; s++) {
-            if (!set_polys[s].empty()) {
+            if (set_count[s]) {
                 Fr zc = host::mul(zt, host::inv(eval_small(zcoef[s], u)));
                 Fr sc = host::mul(vpow, zc);
                 lp.push_back(fbuf + (size_t)s * n);

@@ -197,7 +197,10 @@ private:
 struct BfvParams {          // bfv.rs:27-30 (compile-time consts there)
     size_t N = 1024;
     uint64_t Q = 536870909, T = 7, B = 19;
-    uint64_t delta() const { return Q / T; }     // bfv.rs:112
+    // RNS: one circuit per limb prime proves c0 = pk0*u + delta_i*m + e0 (mod q_i), delta_i = (Q_total / T) mod q_i
+    uint64_t delta_override = 0;
+    bool has_delta_override = false;
+    uint64_t delta() const { return has_delta_override ? delta_override : Q / T; }     // bfv.rs:112
 };
 
 using CircuitInput = std::map<std::string, std::vector<std::string>>;   // bfv.rs:50-61: nine arrays of decimal strings

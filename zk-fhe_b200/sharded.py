@@ -58,6 +58,7 @@ def run(k, proofs, transcript, dist, rank, world, local_rank):
 
     prove_once(bytes(32))                                   # warm-up: one-time allocations
     single, ms_single = timed(proofs)
+    rounds_single = pr.round_ms()
     cats = {}
     if world > 1:
         zd.bind_sharded_prover(ctx, device=torch.device("cuda", local_rank))
@@ -67,6 +68,7 @@ def run(k, proofs, transcript, dist, rank, world, local_rank):
     names = {0: "msm_accumulate", 1: "ntt", 2: "msm_sort", 3: "msm_fold", 4: "msm_final", 7: "collectives"}
     cats = {names[c]: round(ctx.timing(c)[0] / proofs, 3) for c in names}
     comm_calls = ctx.timing(7)[1] // max(proofs, 1)
+    rounds_sharded = pr.round_ms()
     same = torch.tensor([1 if sharded == single else 0], device=torch.device("cuda", local_rank))
     if world > 1:
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
@@ -74,6 +76,7 @@ def run(k, proofs, transcript, dist, rank, world, local_rank):
            "identical_to_single_gpu": bool(same.item()), "proof_bytes": len(sharded),
            "single_gpu_latency_ms": round(float(np.median(ms_single)), 3), "sharded_latency_ms": round(float(np.median(ms_sharded)), 3),
            "speedup": round(float(np.median(ms_single)) / float(np.median(ms_sharded)), 3),
+           "rank0_round_ms_single": rounds_single, "rank0_round_ms_sharded": rounds_sharded,
            "rank0_device_ms_per_sharded_proof": cats, "collectives_per_proof": int(comm_calls),
            "limiters": "replicated on every rank: stage (1) witness kernels, grand products, lagrange->coeff iNTT, evaluations, "
                        "SHPLONK linear combinations, the host transcript (sequential sponge); sharded: MSMs by column, "
