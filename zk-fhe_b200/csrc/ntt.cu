@@ -31,6 +31,7 @@
 // (folded into the 4-step twiddle table for two-pass transforms) and the coset
 // post-multiplication zeta^-(i mod 3).
 #include <cstdlib>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace zkfhe {
@@ -112,9 +113,12 @@ __device__ __forceinline__ void dit_round(fr_t* x, uint32_t j, uint32_t s, uint3
     }
 }
 
-template <int LR>
+// TMA = true (experiment, ZKFHE_NTT_TMA=1): the pass-A tile was brought into shared memory by one cp.async.bulk.tensor
+// (`landing`: R rows x L elements, 32-byte elements, row-major; rows beyond the input are zero-filled by the copy engine)
+// and round 0 gathers its bit-reversed operands from there instead of from global memory.
+template <int LR, bool TMA = false>
 __device__ __forceinline__ void ntt_round(const NttPass& p, uint4* Slo, uint4* Shi, uint32_t s, bool first, bool last,
-                                          const fr_t* __restrict__ in, fr_t* __restrict__ out) {
+                                          const fr_t* __restrict__ in, fr_t* __restrict__ out, const fr_t* landing = nullptr) {
     const uint32_t T = 1u << (p.log_r + p.log_l), lmask = (1u << p.log_l) - 1;
     const uint32_t log_c = p.log_n - p.log_r;          // pass A: columns; pass B: rows of the matrix
     const uint32_t base = blockIdx.x << p.log_l;       // first column (A) / first row (B) of this tile
@@ -130,7 +134,7 @@ __device__ __forceinline__ void ntt_round(const NttPass& p, uint4* Slo, uint4* S
                 const uint32_t tn = brev(t, p.log_r);                 // DIT consumes its input in bit-reversed order
                 const uint32_t g = p.mode == 0 ? (tn << log_c) + base + l : ((base + l) << p.log_r) + tn;
                 if (g < p.in_len) {
-                    fr_t v = fe_load(in + g);
+                    fr_t v = TMA ? fe_load(landing + ((tn << p.log_l) + l)) : fe_load(in + g);
                     if (p.pre_coset) {
                         const uint32_t m3 = g % 3u;
                         if (m3 == 1) v = mul(v, p.zeta);
@@ -190,6 +194,89 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const NttPass p) {
         s += r;
         if (!last) __syncthreads();
     }
+}
+
+// ---- experiment: pass A with the tile staged by TMA (cp.async.bulk.tensor + mbarrier) -------------------------------
+// VERDICT r1 asked for the measurement: does staging the R x L tile through the copy engine beat the bit-reversed gather
+// of round 0 straight from global memory?  The tile needs its own landing buffer (round 0 permutes across threads, so it
+// cannot run in place without holding every operand in registers), i.e. 64 KB instead of 32 KB of shared memory per CTA
+// and 3 instead of 6 CTAs per SM.  Selected with ZKFHE_NTT_TMA=1; results in profiles/ and DESIGN.md.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(256) k_ntt_pass_tma(const NttPass p, const __grid_constant__ CUtensorMap tmap) {
+    const uint32_t T = 1u << (p.log_r + p.log_l);
+    uint4* Slo = ntt_smem;
+    uint4* Shi = ntt_smem + T;
+    // the copy engine wants a 128-byte aligned destination: round up behind the two planes (128 spare bytes are allocated)
+    fr_t* landing = reinterpret_cast<fr_t*>((reinterpret_cast<uintptr_t>(ntt_smem + 2 * T) + 127) & ~(uintptr_t)127);
+    __shared__ alignas(8) uint64_t mbar;
+    fr_t* out = p.out + (uint64_t)blockIdx.y * p.out_stride;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = T * (uint32_t)sizeof(fr_t);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+        // coordinates: (32-bit word inside the row, row, batch column)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(landing)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((blockIdx.x << p.log_l) * 8u), "r"(0u),
+                       "r"(blockIdx.y), "r"(smem_u32(&mbar))
+                     : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    }
+    uint32_t s = 0;
+    for (uint32_t ri = 0; ri < p.n_rounds; ri++) {
+        const uint32_t r = p.rounds[ri];
+        const bool first = ri == 0, last = ri + 1 == p.n_rounds;
+        if (r == 2) ntt_round<2, true>(p, Slo, Shi, s, first, last, nullptr, out, landing);
+        else if (r == 1) ntt_round<1, true>(p, Slo, Shi, s, first, last, nullptr, out, landing);
+        else ntt_round<0, true>(p, Slo, Shi, s, first, last, nullptr, out, landing);
+        s += r;
+        if (!last) __syncthreads();
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return (EncodeTiledFn)sym;
+    }();
+    return fn;
+}
+// pass A over TMA when the shape allows it (tile rows and 32-byte row segments within the 256-element box limit, the
+// input a whole number of matrix rows); returns false to fall back to the plain kernel
+static bool try_launch_pass_a_tma(zkfhe_ctx* ctx, const NttPass& p, uint32_t tiles, uint32_t batch, int* rc) {
+    const uint32_t R = 1u << p.log_r, L = 1u << p.log_l, C = 1u << (p.log_n - p.log_r);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || p.mode != 0 || R > 256 || L * 8 > 256 || p.in_len % C || p.in == p.out) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)C * 8, (cuuint64_t)(p.in_len / C), batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 32, (cuuint64_t)p.in_stride * 32};      // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {L * 8, R, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap tmap;
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)p.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    const uint32_t T = R * L;
+    const size_t smem = 2 * (size_t)T * sizeof(fr_t) + 128;
+    cudaFuncSetAttribute(k_ntt_pass_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * (int)sizeof(fr_t) + 128);
+    if (T > 2048) return false;
+    const uint32_t threads = T / 8 < 32 ? 32 : (T / 8 > 128 ? 128 : T / 8);
+    k_ntt_pass_tma<<<dim3(tiles, batch), threads, smem, ctx->stream>>>(p, tmap);
+    ctx->launches++;
+    *rc = cudaGetLastError() == cudaSuccess ? ZKFHE_OK : fail(ctx, ZKFHE_ERR_CUDA, "k_ntt_pass_tma launch failed");
+    return true;
 }
 
 // tw4[i] = w^-i * n^-1: the inverse transform's scaling rides on the 4-step twiddle
@@ -269,6 +356,11 @@ static int launch_pass(zkfhe_ctx* ctx, NttPass p, uint32_t tiles, uint32_t batch
         uint64_t prod = elems * eighths / 8;
         if (p.pre_coset) prod += (uint64_t)batch * (p.in_len < (1u << p.log_n) ? p.in_len : (1u << p.log_n)) * 2 / 3;
         ctx->ntt_products += prod;
+    }
+    {
+        static const bool use_tma = [] { const char* e = getenv("ZKFHE_NTT_TMA"); return e && atoi(e) != 0; }();
+        int rc = ZKFHE_OK;
+        if (use_tma && try_launch_pass_a_tma(ctx, p, tiles, batch, &rc)) return rc;
     }
     dim3 grid(tiles, batch);
     k_ntt_pass<<<grid, threads, smem, ctx->stream>>>(p);
