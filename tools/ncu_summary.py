@@ -7,8 +7,8 @@ import sys
 KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',      # IMAD.WIDE issues here only: the binding pipe
-        'sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',     # IMAD.WIDE issues here only: the binding pipe
+        'sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',

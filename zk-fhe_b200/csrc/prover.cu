@@ -177,6 +177,7 @@ struct GpArgs {
     const fr_t* delta_pow;
     const fr_t* tw;          // w^i
     const fr_t* blind;       // [n_chunks + n_lookup][n - usable - 1] blinding rows of the Z columns
+    uint32_t z_base;         // first Z column of this launch (a shard computes a block of them)
     fr_t beta, gamma;
 };
 static constexpr uint32_t GP_THREADS = 1024, GP_PER = 8;     // one tile = 8192 rows; columns are walked tile by tile
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_grand_product(const GpArgs g) {
     fr_t* S = reinterpret_cast<fr_t*>(gp_smem);      // [4][GP_THREADS]: two double-buffered scans
     __shared__ fr_t tile_carry;                      // product of all ratios of the previous tiles
     __shared__ fr_t tile_inv;                        // 1 / (product of this tile's denominators)
-    const uint32_t z = blockIdx.x;                   // 0..n_chunks-1: permutation chunks, then lookups
+    const uint32_t z = blockIdx.x + g.z_base;        // 0..n_chunks-1: permutation chunks, then lookups
     const bool is_perm = z < g.n_chunks;
     const uint32_t tid = threadIdx.x;
     fr_t* Z = g.P + (uint64_t)(is_perm ? g.zp_base + z : g.zl_base + (z - g.n_chunks)) * g.n;
@@ -690,7 +691,8 @@ int zkfhe_prove_begin(zkfhe_ctx* ctx, zkfhe_pk* pk, const uint8_t* seed32, int t
     pr->r_col = pr->zl_base + pk->n_lookup;
     pr->C_all = pr->r_col + 1;
     const size_t n = pk->n;
-    cudaError_t e = cudaMalloc(&pr->P, (size_t)pr->C_all * n * 32);
+    // (+64 columns: an all-gather of the last round's columns in blocks of ceil(count / ranks) may run past C_all)
+    cudaError_t e = cudaMalloc(&pr->P, ((size_t)pr->C_all + 64) * n * 32);
     if (e == cudaSuccess) e = cudaMalloc(&pr->E, ((size_t)pr->C_all * n * 32) << EXT_SHIFT);
     if (e == cudaSuccess) e = cudaMalloc(&pr->inst, n * 32);
     if (e == cudaSuccess) e = cudaMalloc(&pr->inst_ext, (n * 32) << EXT_SHIFT);
@@ -827,8 +829,22 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         g.delta_pow = pk->delta_pow; g.tw = dom->tw_fwd; g.blind = pr->blind; g.beta = dev(pr->beta); g.gamma = dev(pr->gamma);
         const size_t smem = 4 * GP_THREADS * sizeof(fr_t);
         ZK_CUDA(ctx, cudaFuncSetAttribute(k_grand_product, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_grand_product<<<nz, GP_THREADS, smem, ctx->stream>>>(g);
-        ZK_CHECK_LAUNCH(ctx);
+        // the nz + 1 columns of this round (Z_perm | Z_lookup | R) are split into the same contiguous blocks the
+        // commitments are: a shard computes the grand products it commits, the Lagrange columns are all-gathered in place
+        // in P (every rank needs every Z later: the chain of the permutation products, the quotient, the openings)
+        const Shards sh = shards_of(ctx);
+        const uint32_t per = shard_per(nz + 1, sh.G);
+        for (uint32_t v = sh.first; v < sh.last; v++) {
+            uint32_t lo, hi;
+            shard_range(nz + 1, sh.G, v, &lo, &hi);
+            if (hi > nz) hi = nz;                          // the last column of the round is R, not a product
+            if (hi > lo) {
+                g.z_base = lo;
+                k_grand_product<<<hi - lo, GP_THREADS, smem, ctx->stream>>>(g);
+                ZK_CHECK_LAUNCH(ctx);
+            }
+        }
+        ZK_TRY(comm_allgather(ctx, pr->P + (size_t)pr->zp_base * n, (size_t)per * n * 32));
         fr_t* carry = pr->misc;
         k_perm_chain_carry<<<1, 1, 0, ctx->stream>>>(pr->P, n, pr->zp_base, pk->n_chunks, usable, carry);
         ZK_CHECK_LAUNCH(ctx);
