@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transcript", type=int, default=1, help="1 Poseidon (default: the reference's transcript), 0 BLAKE2b")
+    ap.add_argument("--spin", action="store_true", help="spinning host waits (cudaStreamSynchronize) instead of blocking events")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof-over-N-GPUs latency measurement")
     ap.add_argument("--streams", type=int, default=16, help="proofs in flight per GPU (one CUDA stream + host thread each)")
     args = ap.parse_args()
@@ -377,6 +378,7 @@ def main():
             self.ctx = ctx if index == 0 else zk_fhe_b200.Context(local_rank)
             if index:
                 self.ctx.share_srs(ctx)
+            self.ctx.set_blocking_sync(not args.spin)
             self.circ = bfv.BfvCircuit(self.ctx, params)
             self.resident = [self.circ.upload(inp) for inp in inputs]
             self.pr = prover.Prover(pk, bytes(32), args.transcript, ctx=self.ctx)

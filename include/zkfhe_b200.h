@@ -62,6 +62,10 @@ const char* zkfhe_version(void);
  * stream).  Until this is called the context uses a private non-blocking stream. */
 int zkfhe_set_stream(zkfhe_ctx* ctx, void* cuda_stream);
 int zkfhe_sync(zkfhe_ctx* ctx);
+/* How the host thread waits for the stream inside the library (commitment read-backs, status checks): on != 0
+ * (default) sleeps on a blocking-sync CUDA event, leaving the core to the other proofs' host work (the transcript's
+ * Poseidon sponge); 0 spins in cudaStreamSynchronize, a few microseconds quicker per wait for a lone proof. */
+int zkfhe_set_blocking_sync(zkfhe_ctx* ctx, int on);
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */
 uint64_t zkfhe_launch_count(const zkfhe_ctx* ctx);
 /* On-device self test of the generated PTX field arithmetic against an independent plain-C

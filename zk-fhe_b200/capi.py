@@ -45,6 +45,7 @@ _SIGNATURES = {
     "zkfhe_version": (_c.c_char_p, []),
     "zkfhe_set_stream": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "zkfhe_sync": (_c.c_int, [_c.c_void_p]),
+    "zkfhe_set_blocking_sync": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "zkfhe_launch_count": (_c.c_uint64, [_c.c_void_p]),
     "zkfhe_selftest": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint64, _c.POINTER(_c.c_uint32)]),
     "zkfhe_pairing_check": (_c.c_int, [_u8p, _u8p, _c.c_uint32, _c.POINTER(_c.c_int)]),
@@ -242,6 +243,10 @@ class Context:
 
     def sync(self):
         self._check(self.lib.zkfhe_sync(self.h))
+
+    def set_blocking_sync(self, on):
+        """Host waits inside the library sleep on a blocking event (True, default) or spin (False)."""
+        self._check(self.lib.zkfhe_set_blocking_sync(self.h, int(bool(on))))
 
     def status(self):
         """Synchronise and raise if a data-dependent reference assert fired on the device."""

@@ -93,7 +93,7 @@ int selftest_run(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mism
     k_selftest<<<(n_cases + 127) / 128, 128, 0, ctx->stream>>>(n_cases, seed, d_bad);
     ZK_CHECK_LAUNCH(ctx);
     ZK_CUDA(ctx, cudaMemcpyAsync(mismatches, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     ZK_CUDA(ctx, cudaFree(d_bad));
     return ZKFHE_OK;
 }
@@ -264,6 +264,7 @@ void zkfhe_destroy(zkfhe_ctx* ctx) {
     for (auto& b : ctx->basis) if (b.table && !b.shared) { cudaFree(b.table); if (b.table_s) cudaFree(b.table_s); }
     for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -272,16 +273,22 @@ const char* zkfhe_last_error(const zkfhe_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int zkfhe_set_stream(zkfhe_ctx* ctx, void* cuda_stream) {
     if (!ctx) return ZKFHE_ERR_ARG;
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;     // NULL is the CUDA legacy default stream
     ctx->own_stream = false;
     return ZKFHE_OK;
 }
 
+int zkfhe_set_blocking_sync(zkfhe_ctx* ctx, int on) {
+    if (!ctx) return ZKFHE_ERR_ARG;
+    ctx->blocking_sync = on != 0;
+    return ZKFHE_OK;
+}
+
 int zkfhe_sync(zkfhe_ctx* ctx) {
     if (!ctx) return ZKFHE_ERR_ARG;
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -303,7 +310,7 @@ float zkfhe_last_kernel_ms(const zkfhe_ctx* ctx) {
 
 int zkfhe_timing_reset(zkfhe_ctx* ctx) {
     if (!ctx) return ZKFHE_ERR_ARG;
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     ctx->ev_used = ctx->call_mark = 0;
     ctx->ntt_products = 0;
     auto it = ctx->ws.find("msm_refs");
@@ -317,7 +324,7 @@ int zkfhe_timing_get(zkfhe_ctx* ctx, int category, float* ms, uint32_t* spans, u
         unsigned long long v = 0;
         auto it = ctx->ws.find("msm_refs");
         if (it != ctx->ws.end()) {
-            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
             ZK_CUDA(ctx, cudaMemcpy(&v, it->second.p, 8, cudaMemcpyDeviceToHost));
         }
         if (ms) *ms = 0.f;
@@ -381,7 +388,7 @@ int zkfhe_ntt_fr(zkfhe_ctx* ctx, uint8_t* h_data, uint32_t log_n, uint32_t batch
     ZK_CUDA(ctx, cudaMemcpyAsync(d, h_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ZK_TRY(zkfhe_ntt_fr_dev(ctx, (uint8_t*)d, log_n, batch, inverse, coset));
     ZK_CUDA(ctx, cudaMemcpyAsync(h_data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -431,7 +438,7 @@ int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t
     if (h_g_out) ZK_CUDA(ctx, cudaMemcpyAsync(h_g_out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_g_lagrange_out)
         ZK_CUDA(ctx, cudaMemcpyAsync(h_g_lagrange_out, d + ((size_t)1 << k), bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -486,7 +493,7 @@ int zkfhe_msm_g1(zkfhe_ctx* ctx, const uint8_t* h_scalars, uint32_t batch, int b
     ZK_CUDA(ctx, cudaMemcpyAsync(d_s, h_scalars, sbytes, cudaMemcpyHostToDevice, ctx->stream));
     ZK_TRY(zkfhe_msm_g1_dev(ctx, (const uint8_t*)d_s, batch, basis, (uint8_t*)d_o));
     ZK_CUDA(ctx, cudaMemcpyAsync(h_out_affine, d_o, obytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 

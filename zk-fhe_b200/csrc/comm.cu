@@ -105,7 +105,7 @@ int zkfhe_comm_destroy(zkfhe_ctx* ctx) {
     if (!ctx) return ZKFHE_ERR_ARG;
     if (ctx->nccl_comm) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        zkfhe::stream_wait(ctx);
         nccl()->CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }

@@ -70,6 +70,11 @@ struct zkfhe_ctx {
     int virtual_ranks = 0;
     float comm_ms = 0;                           // device time spent in collectives since timing_reset (category 7)
     uint32_t comm_calls = 0;
+    // host waits: by default the calling thread SLEEPS on a blocking-sync event until the stream has drained (many
+    // proofs in flight share the host cores with the transcript's Poseidon sponge; cudaStreamSynchronize would spin a
+    // core per waiting thread); zkfhe_set_blocking_sync(ctx, 0) switches back to the spinning wait for lowest latency
+    bool blocking_sync = true;
+    cudaEvent_t sync_event = nullptr;
 };
 enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4,
        ZK_CAT_MSM_REFS = 5 /* no time: units = point additions issued by the accumulate kernel */, 
@@ -77,6 +82,16 @@ enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_M
        ZK_CAT_COMM = 7 /* NCCL collectives of a sharded proof (units = bytes gathered) */, ZK_CAT_COUNT = 8 };
 
 namespace zkfhe {
+
+inline cudaError_t stream_wait(zkfhe_ctx* ctx) {
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+    if (!ctx->sync_event) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_event);
+}
 
 inline int fail(zkfhe_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -138,7 +153,7 @@ inline int ws_get(zkfhe_ctx* ctx, const char* name, size_t bytes, void** out) {
     DevBuf& b = ctx->ws[name];
     if (b.bytes < bytes) {
         if (b.p) {
-            ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ZK_CUDA(ctx, stream_wait(ctx));
             ZK_CUDA(ctx, cudaFree(b.p));
             b.p = nullptr;
             b.bytes = 0;

@@ -103,7 +103,7 @@ static int pk_finalize(zkfhe_pk* pk) {
     ZK_CUDA(ctx, cudaMemcpyAsync(pk->fixed_coeff, pk->fixed_lagrange, fbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_coeff, n, k, pk->n_fixed, 1, 0));
     ZK_TRY(ntt_run(ctx, pk->fixed_coeff, n, n, pk->fixed_ext, (uint64_t)n << EXT_SHIFT, k + EXT_SHIFT, pk->n_fixed, 0, 1));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
 
     // ---- pinning (configs/<name>.json schema of the reference) and vk digest -----------------------------
     pk->pinning_json =
@@ -192,7 +192,7 @@ int zkfhe_keygen(zkfhe_witness* w, uint32_t k, uint32_t unusable_rows, zkfhe_pk*
         lk_src.resize(off + m);
         if (m) ZK_CUDA(ctx, cudaMemcpyAsync(lk_src.data() + off, w->lk_src[c].p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     pk->lookups = lk_src.size();
     pk->instances = w->make_public.size();
     for (auto& c : w->make_public) pk->public_cells.push_back(cell_id(c.ctx_id, c.offset));
@@ -368,7 +368,7 @@ int zkfhe_pk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed
     put(pk->fixed_commitments.data(), (size_t)pk->n_fixed * 64);
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     ZK_CUDA(ctx, cudaMemcpyAsync(p, pk->fixed_lagrange, (size_t)pk->n_fixed * pk->n * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -484,7 +484,7 @@ int zkfhe_pk_download_fixed(const zkfhe_pk* pk, uint32_t index, uint32_t form, u
     const fr_t* src = form == 0 ? pk->fixed_lagrange + index * n : form == 1 ? pk->fixed_coeff + index * n
                                                                            : pk->fixed_ext + ((index * n) << EXT_SHIFT);
     ZK_CUDA(ctx, cudaMemcpyAsync(h_out, src, (form == 2 ? n << EXT_SHIFT : n) * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 

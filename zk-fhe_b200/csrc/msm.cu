@@ -692,7 +692,7 @@ int msm_load_basis(zkfhe_ctx* ctx, int which, const g1_affine* d_bases, uint32_t
         B.W_s = (255 + B.c_s - 1) / B.c_s;
         ZK_TRY(build_table(ctx, d_bases, n, B.c_s, B.W_s, B.prefix, &B.table_s));
     }
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     B.loaded = true;
     return ZKFHE_OK;
 }
@@ -838,7 +838,7 @@ int msm_variable_base(zkfhe_ctx* ctx, const g1_affine* h_points, const fr_t* h_s
     if (rc == ZKFHE_OK) rc = msm_run(ctx, d_sc, n, log_n, 1, 0, d_out, 0);
     if (rc == ZKFHE_OK && cudaMemcpyAsync(h_out, d_out, sizeof(g1_affine), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
         rc = fail(ctx, ZKFHE_ERR_CUDA, "msm_variable_base: copy back failed");
-    cudaStreamSynchronize(ctx->stream);
+    zkfhe::stream_wait(ctx);
     if (ctx->basis[0].table) cudaFree(ctx->basis[0].table);
     if (ctx->basis[0].table_s) cudaFree(ctx->basis[0].table_s);
     ctx->basis[0] = saved;

@@ -306,7 +306,7 @@ int ntt_domain(zkfhe_ctx* ctx, uint32_t log_n, NttDomain** out) {
     k_scale_twiddles<<<blocks, 256, 0, ctx->stream>>>(d.tw_inv, d.tw_inv_s, (uint32_t)n, d_ninv);
     ZK_CHECK_LAUNCH(ctx);
     ZK_CUDA(ctx, cudaMemcpyAsync(&d.n_inv, d_ninv, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     ZK_CUDA(ctx, cudaFree(d_ninv));
     ctx->domains[log_n] = d;
     *out = &ctx->domains[log_n];

@@ -616,7 +616,7 @@ static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count
     ZK_TRY(points_to_canonical(ctx, d_pts, count));
     std::vector<std::array<uint64_t, 8>> h(count);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pts, (size_t)count * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     for (auto& p : h) pr->tr.write_point(p.data(), p.data() + 4);
     return ZKFHE_OK;
 }
@@ -732,7 +732,7 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     std::vector<Fr> h_inst(pk->instances);
     if (pk->instances)
         ZK_CUDA(ctx, cudaMemcpyAsync(h_inst.data(), pr->inst, pk->instances * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     pr->tr.common_scalar(pk->vk_digest);
     for (auto& v : h_inst) pr->tr.common_scalar(v);
     // phase-0 advice columns
@@ -802,7 +802,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->ap_base * n, 2 * pk->n_lookup, 1, 1));
         uint32_t st = 0;
         ZK_CUDA(ctx, cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
         if (st & (1u << 6)) {
             k_status_clear_bits<<<1, 1, 0, ctx->stream>>>(status, 1u << 6);      // other recorded asserts stay for zkfhe_status
             ZK_CHECK_LAUNCH(ctx);
@@ -996,7 +996,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(comm_allgather(ctx, d_out, max_t * 32));
         std::vector<Fr> flat(sh.G * max_t);
         ZK_CUDA(ctx, cudaMemcpyAsync(flat.data(), d_out, flat.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
         std::vector<size_t> next(sh.G, 0);
         size_t ei = 0;
         for (auto& p : polys)

@@ -55,7 +55,7 @@ static int vec_reserve(zkfhe_ctx* ctx, DevVec& v, size_t need) {
     ZK_CUDA(ctx, cudaMalloc(&np, ncap * sizeof(fr_t)));
     if (v.size) ZK_CUDA(ctx, cudaMemcpyAsync(np, v.p, v.size * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
     if (v.p) {
-        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
         ZK_CUDA(ctx, cudaFree(v.p));
     }
     v.p = np;
@@ -71,7 +71,7 @@ template <class T> static int arr_reserve(zkfhe_ctx* ctx, DevArr<T>& a, size_t c
     ZK_CUDA(ctx, cudaMemsetAsync(np, 0, cap * sizeof(T), ctx->stream));
     if (used && a.p) ZK_CUDA(ctx, cudaMemcpyAsync(np, a.p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     if (a.p) {
-        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
         ZK_CUDA(ctx, cudaFree(a.p));
     }
     a.p = np;
@@ -493,7 +493,7 @@ int zkfhe_status(zkfhe_ctx* ctx) {
     ZK_TRY(status_word(ctx, &status));
     uint32_t h = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&h, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     h &= 0xffffu;
     if (h == 0) return ZKFHE_OK;
     ZK_CUDA(ctx, cudaMemsetAsync(status, 0, 4, ctx->stream));
@@ -514,7 +514,7 @@ int zkfhe_poly_from_u64(zkfhe_ctx* ctx, const uint64_t* h_coeffs, uint32_t len, 
     k_poly_from_u64<<<blocks_for(len), 128, 0, ctx->stream>>>((const uint64_t*)stage, (*out)->d, len, modulus, status);
     ZK_CHECK_LAUNCH(ctx);
     // the staging buffer is reused by the next call: make the copy-in safe against host reuse too
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -557,7 +557,7 @@ int zkfhe_poly_from_u256(zkfhe_ctx* ctx, const uint64_t* h, uint32_t len, uint64
     ZK_CUDA(ctx, cudaMemcpyAsync((*out)->d, h, (size_t)len * 32, cudaMemcpyHostToDevice, ctx->stream));
     k_poly_check_bits<<<blocks_for(len), 128, 0, ctx->stream>>>((*out)->d, len, (uint32_t)(max_bits > 256 ? 256 : max_bits), status);
     ZK_CHECK_LAUNCH(ctx);
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -638,7 +638,7 @@ int zkfhe_poly_download(zkfhe_ctx* ctx, const zkfhe_poly* p, uint64_t* h_out) {
     if (!ctx || !p || !h_out) return fail(ctx, ZKFHE_ERR_ARG, "poly_download: null pointer");
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     ZK_CUDA(ctx, cudaMemcpyAsync(h_out, p->d, (size_t)p->len * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -693,7 +693,7 @@ int zkfhe_witness_download_structure(zkfhe_witness* w, uint32_t ctx_id, uint8_t*
     const size_t n = w->adv[ctx_id].size;
     if (n && h_flags) ZK_CUDA(ctx, cudaMemcpyAsync(h_flags, w->flags[ctx_id].p, n, cudaMemcpyDeviceToHost, ctx->stream));
     if (n && h_copy) ZK_CUDA(ctx, cudaMemcpyAsync(h_copy, w->copy[ctx_id].p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -708,7 +708,7 @@ int zkfhe_witness_download_lookup_sources(zkfhe_witness* w, uint64_t* h_src) {
             ZK_CUDA(ctx, cudaMemcpyAsync(h_src + off, w->lk_src[i].p, w->lk[i].size * 8, cudaMemcpyDeviceToHost, ctx->stream));
         off += w->lk[i].size;
     }
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -788,7 +788,7 @@ int zkfhe_witness_mock(zkfhe_witness* w, uint64_t* n_violations, uint64_t* first
     }
     unsigned long long res[2];
     ZK_CUDA(ctx, cudaMemcpyAsync(res, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     *n_violations = res[0];
     if (first_bad_cell) *first_bad_cell = res[1];
     if (res[0]) {
@@ -936,7 +936,7 @@ int zkfhe_chip_reduce_by_modulo(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe
     k_to_mont_one<<<1, 1, 0, ctx->stream>>>(d_bound);
     ZK_CHECK_LAUNCH(ctx);
     ZK_CUDA(ctx, cudaMemcpyAsync(&hb, d_bound, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_gate, a->len, per, &o, &base));
@@ -1100,7 +1100,7 @@ int zkfhe_witness_download(zkfhe_witness* w, uint32_t which, uint8_t* h_out) {
     } else {
         return fail(ctx, ZKFHE_ERR_ARG, "download: which=%u out of range", which);
     }
-    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
