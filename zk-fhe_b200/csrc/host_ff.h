@@ -135,11 +135,481 @@ inline Fr mul_adx(const Fr& a, const Fr& b) {
 }
 #undef ZK_MM_ROUND
 #undef ZK_MM_MULADD
+// sum_{j<5} m[j] * s[j] (Montgomery) with ONE reduction: the five 512-bit products are accumulated in eight registers
+// (5 r^2 < r * 2^256, so the sum is a valid REDC input and the result is < 2r) -- 96 mulx instead of 160 for the rows of
+// the MDS / sparse matrices, which are 60 % of the permutation's products.  (text generated by a ten-line script: 24 rows of mulx + adox/adcx with carry ripple).
+inline Fr dot5_adx(const Fr* m, const Fr* s) {
+    Fr o;
+    __asm__ volatile(
+        "xorl %%ecx, %%ecx\n\t"
+        "xorl %%r8d, %%r8d\n\t"
+        "xorl %%r9d, %%r9d\n\t"
+        "xorl %%r10d, %%r10d\n\t"
+        "xorl %%r11d, %%r11d\n\t"
+        "xorl %%r12d, %%r12d\n\t"
+        "xorl %%r13d, %%r13d\n\t"
+        "xorl %%r14d, %%r14d\n\t"
+        "xorl %%r15d, %%r15d\n\t"
+        "movq 0(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 8(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 16(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 24(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 32(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 40(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 48(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 56(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 64(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 72(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 80(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 88(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 96(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 104(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 112(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 120(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 128(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 128(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 136(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 144(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 152(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 136(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 128(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 136(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 144(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 152(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 144(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 128(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 136(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 144(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 152(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq 152(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 128(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 136(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 144(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 152(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq %%r8, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %%rcx, %%r12\n\t"
+        "adcxq %%rcx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq %%r9, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %%rcx, %%r13\n\t"
+        "adcxq %%rcx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq %%r10, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %%rcx, %%r14\n\t"
+        "adcxq %%rcx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq %%r11, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %%rcx, %%r15\n\t"
+        "movq %%r12, %%r8\n\t"
+        "movq %%r13, %%r9\n\t"
+        "movq %%r14, %%r10\n\t"
+        "movq %%r15, %%r11\n\t"
+        "subq %[q0], %%r8\n\t"
+        "sbbq %[q1], %%r9\n\t"
+        "sbbq %[q2], %%r10\n\t"
+        "sbbq %[q3], %%r11\n\t"
+        "cmovcq %%r12, %%r8\n\t"
+        "cmovcq %%r13, %%r9\n\t"
+        "cmovcq %%r14, %%r10\n\t"
+        "cmovcq %%r15, %%r11\n\t"
+        "movq %%r8, 0(%[o])\n\t"
+        "movq %%r9, 8(%[o])\n\t"
+        "movq %%r10, 16(%[o])\n\t"
+        "movq %%r11, 24(%[o])\n\t"
+        :
+        : [m] "r"(m), [s] "r"(s), [o] "r"(o.l), [q0] "m"(FR_MOD.l[0]), [q1] "m"(FR_MOD.l[1]), [q2] "m"(FR_MOD.l[2]), [q3] "m"(FR_MOD.l[3]),
+          [inv] "m"(FR_INV)
+        : "rax", "rbx", "rcx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+    return o;
+}
 inline bool cpu_has_adx() {
     static const bool ok = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx");
     return ok;
 }
 inline Fr mul(const Fr& a, const Fr& b) { return cpu_has_adx() ? mul_adx(a, b) : mul_portable(a, b); }
+#define ZKFHE_HAVE_DOT5_ADX 1
 #else
 inline Fr mul(const Fr& a, const Fr& b) { return mul_portable(a, b); }
 #endif
@@ -180,13 +650,19 @@ inline Fr omega(uint32_t k) {   // generator of the 2^k-th roots of unity (Montg
 // oracle (which is pinned by the published t = 3 / t = 2 vectors).
 inline const Fr& pc(const uint64_t (*tbl)[4], size_t i) { return *(const Fr*)tbl[i]; }
 inline Fr pow5(const Fr& x) { Fr x2 = sqr(x); return mul(sqr(x2), x); }
+// <row of five matrix entries, state>: one lazily reduced dot product where the CPU has BMI2 / ADX
+static_assert(POSEIDON_T == 5, "dot5 is written for the t = 5 instance");
+inline Fr dot5(const uint64_t (*m)[4], size_t first, const Fr s[POSEIDON_T]) {
+#ifdef ZKFHE_HAVE_DOT5_ADX
+    if (cpu_has_adx()) return dot5_adx((const Fr*)m[first], s);
+#endif
+    Fr acc = mul(pc(m, first), s[0]);
+    for (int j = 1; j < POSEIDON_T; j++) acc = add(acc, mul(pc(m, first + j), s[j]));
+    return acc;
+}
 inline void poseidon_mds(Fr s[POSEIDON_T], const uint64_t (*m)[4]) {
     Fr n[POSEIDON_T];
-    for (int i = 0; i < POSEIDON_T; i++) {
-        Fr acc = mul(pc(m, i * POSEIDON_T), s[0]);
-        for (int j = 1; j < POSEIDON_T; j++) acc = add(acc, mul(pc(m, i * POSEIDON_T + j), s[j]));
-        n[i] = acc;
-    }
+    for (int i = 0; i < POSEIDON_T; i++) n[i] = dot5(m, (size_t)i * POSEIDON_T, s);
     for (int i = 0; i < POSEIDON_T; i++) s[i] = n[i];
 }
 inline void poseidon_permute(Fr s[POSEIDON_T]) {
@@ -199,8 +675,7 @@ inline void poseidon_permute(Fr s[POSEIDON_T]) {
         s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
         if (r + 1 < POSEIDON_RP) {
             const size_t b = (size_t)r * (2 * T - 1);
-            Fr n0 = mul(pc(POSEIDON_SPARSE, b), s[0]);
-            for (int j = 1; j < T; j++) n0 = add(n0, mul(pc(POSEIDON_SPARSE, b + j), s[j]));
+            const Fr n0 = dot5(POSEIDON_SPARSE, b, s);
             for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
             s[0] = n0;
         } else {
