@@ -138,10 +138,10 @@ inline Fr mul_adx(const Fr& a, const Fr& b) {
 // sum_{j<5} m[j] * s[j] (Montgomery) with ONE reduction: the five 512-bit products are accumulated in eight registers
 // (5 r^2 < r * 2^256, so the sum is a valid REDC input and the result is < 2r) -- 96 mulx instead of 160 for the rows of
 // the MDS / sparse matrices, which are 60 % of the permutation's products.  (text generated by a ten-line script: 24 rows of mulx + adox/adcx with carry ripple).
+static const uint64_t FR_ZERO_WORD = 0;
 inline Fr dot5_adx(const Fr* m, const Fr* s) {
     Fr o;
     __asm__ volatile(
-        "xorl %%ecx, %%ecx\n\t"
         "xorl %%r8d, %%r8d\n\t"
         "xorl %%r9d, %%r9d\n\t"
         "xorl %%r10d, %%r10d\n\t"
@@ -164,13 +164,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 24(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 8(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 0(%[m]), %%rax, %%rbx\n\t"
@@ -185,11 +185,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 24(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 16(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 0(%[m]), %%rax, %%rbx\n\t"
@@ -204,9 +204,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 24(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 24(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 0(%[m]), %%rax, %%rbx\n\t"
@@ -221,7 +221,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 24(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 32(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 32(%[m]), %%rax, %%rbx\n\t"
@@ -236,13 +236,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 56(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 40(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 32(%[m]), %%rax, %%rbx\n\t"
@@ -257,11 +257,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 56(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 48(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 32(%[m]), %%rax, %%rbx\n\t"
@@ -276,9 +276,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 56(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 56(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 32(%[m]), %%rax, %%rbx\n\t"
@@ -293,7 +293,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 56(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 64(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 64(%[m]), %%rax, %%rbx\n\t"
@@ -308,13 +308,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 88(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 72(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 64(%[m]), %%rax, %%rbx\n\t"
@@ -329,11 +329,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 88(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 80(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 64(%[m]), %%rax, %%rbx\n\t"
@@ -348,9 +348,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 88(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 88(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 64(%[m]), %%rax, %%rbx\n\t"
@@ -365,7 +365,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 88(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 96(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 96(%[m]), %%rax, %%rbx\n\t"
@@ -380,13 +380,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 120(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 104(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 96(%[m]), %%rax, %%rbx\n\t"
@@ -401,11 +401,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 120(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 112(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 96(%[m]), %%rax, %%rbx\n\t"
@@ -420,9 +420,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 120(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 120(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 96(%[m]), %%rax, %%rbx\n\t"
@@ -437,7 +437,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 120(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 128(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 128(%[m]), %%rax, %%rbx\n\t"
@@ -452,13 +452,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 152(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 136(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 128(%[m]), %%rax, %%rbx\n\t"
@@ -473,11 +473,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 152(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 144(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 128(%[m]), %%rax, %%rbx\n\t"
@@ -492,9 +492,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 152(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq 152(%[s]), %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq 128(%[m]), %%rax, %%rbx\n\t"
@@ -509,7 +509,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq 152(%[m]), %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq %%r8, %%rdx\n\t imulq %[inv], %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq %[q0], %%rax, %%rbx\n\t"
@@ -524,13 +524,13 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq %[q3], %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r11\n\t"
         "adcxq %%rbx, %%r12\n\t"
-        "adoxq %%rcx, %%r12\n\t"
-        "adcxq %%rcx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq %%r9, %%rdx\n\t imulq %[inv], %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq %[q0], %%rax, %%rbx\n\t"
@@ -545,11 +545,11 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq %[q3], %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r12\n\t"
         "adcxq %%rbx, %%r13\n\t"
-        "adoxq %%rcx, %%r13\n\t"
-        "adcxq %%rcx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq %%r10, %%rdx\n\t imulq %[inv], %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq %[q0], %%rax, %%rbx\n\t"
@@ -564,9 +564,9 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq %[q3], %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r13\n\t"
         "adcxq %%rbx, %%r14\n\t"
-        "adoxq %%rcx, %%r14\n\t"
-        "adcxq %%rcx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq %%r11, %%rdx\n\t imulq %[inv], %%rdx\n\t"
         "xorl %%eax, %%eax\n\t"
         "mulxq %[q0], %%rax, %%rbx\n\t"
@@ -581,7 +581,7 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "mulxq %[q3], %%rax, %%rbx\n\t"
         "adoxq %%rax, %%r14\n\t"
         "adcxq %%rbx, %%r15\n\t"
-        "adoxq %%rcx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
         "movq %%r12, %%r8\n\t"
         "movq %%r13, %%r9\n\t"
         "movq %%r14, %%r10\n\t"
@@ -600,8 +600,500 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         "movq %%r11, 24(%[o])\n\t"
         :
         : [m] "r"(m), [s] "r"(s), [o] "r"(o.l), [q0] "m"(FR_MOD.l[0]), [q1] "m"(FR_MOD.l[1]), [q2] "m"(FR_MOD.l[2]), [q3] "m"(FR_MOD.l[3]),
-          [inv] "m"(FR_INV)
-        : "rax", "rbx", "rcx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+          [inv] "m"(FR_INV), [zero] "m"(FR_ZERO_WORD)
+        : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+    return o;
+}
+// The two halves of a lazily reduced dot product, for the partial rounds: `dot4_acc_adx` accumulates the four products
+// that do not involve state[0] (512 bits, unreduced) and can therefore be issued BEFORE the S-box chain on state[0]
+// in program order; `fma_redc_adx` adds m * s to that accumulator and reduces once.  The out-of-order core then runs
+// the three dependent products of the S-box underneath the four independent ones.
+struct Acc512 { uint64_t l[8]; };
+inline void dot4_acc_adx(const Fr* m, const Fr* s, Acc512& out) {
+    __asm__ volatile(
+        "xorl %%r8d, %%r8d\n\t"
+        "xorl %%r9d, %%r9d\n\t"
+        "xorl %%r10d, %%r10d\n\t"
+        "xorl %%r11d, %%r11d\n\t"
+        "xorl %%r12d, %%r12d\n\t"
+        "xorl %%r13d, %%r13d\n\t"
+        "xorl %%r14d, %%r14d\n\t"
+        "xorl %%r15d, %%r15d\n\t"
+        "movq 0(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 8(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 16(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 24(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 32(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 40(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 48(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 56(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 64(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 72(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 80(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 88(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 96(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 104(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 112(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 120(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r8, 0(%[o])\n\t"
+        "movq %%r9, 8(%[o])\n\t"
+        "movq %%r10, 16(%[o])\n\t"
+        "movq %%r11, 24(%[o])\n\t"
+        "movq %%r12, 32(%[o])\n\t"
+        "movq %%r13, 40(%[o])\n\t"
+        "movq %%r14, 48(%[o])\n\t"
+        "movq %%r15, 56(%[o])\n\t"
+        :
+        : [m] "r"(m), [s] "r"(s), [o] "r"(out.l), [zero] "m"(FR_ZERO_WORD)
+        : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+}
+inline Fr fma_redc_adx(Acc512& acc, const Fr* m, const Fr* s) {        // the reduced sum lands in acc.l[0..3]
+    __asm__ volatile(
+        "movq 0(%[acc]), %%r8\n\t"
+        "movq 8(%[acc]), %%r9\n\t"
+        "movq 16(%[acc]), %%r10\n\t"
+        "movq 24(%[acc]), %%r11\n\t"
+        "movq 32(%[acc]), %%r12\n\t"
+        "movq 40(%[acc]), %%r13\n\t"
+        "movq 48(%[acc]), %%r14\n\t"
+        "movq 56(%[acc]), %%r15\n\t"
+        "movq 0(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 8(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 16(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq 24(%[s]), %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r8, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r8\n\t"
+        "adcxq %%rbx, %%r9\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "adoxq %[zero], %%r12\n\t"
+        "adcxq %[zero], %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r9, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r9\n\t"
+        "adcxq %%rbx, %%r10\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "adoxq %[zero], %%r13\n\t"
+        "adcxq %[zero], %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r10, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r10\n\t"
+        "adcxq %%rbx, %%r11\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "adoxq %[zero], %%r14\n\t"
+        "adcxq %[zero], %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r11, %%rdx\n\t imulq %[inv], %%rdx\n\t"
+        "xorl %%eax, %%eax\n\t"
+        "mulxq %[q0], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r11\n\t"
+        "adcxq %%rbx, %%r12\n\t"
+        "mulxq %[q1], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r12\n\t"
+        "adcxq %%rbx, %%r13\n\t"
+        "mulxq %[q2], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r13\n\t"
+        "adcxq %%rbx, %%r14\n\t"
+        "mulxq %[q3], %%rax, %%rbx\n\t"
+        "adoxq %%rax, %%r14\n\t"
+        "adcxq %%rbx, %%r15\n\t"
+        "adoxq %[zero], %%r15\n\t"
+        "movq %%r12, %%r8\n\t"
+        "movq %%r13, %%r9\n\t"
+        "movq %%r14, %%r10\n\t"
+        "movq %%r15, %%r11\n\t"
+        "subq %[q0], %%r8\n\t"
+        "sbbq %[q1], %%r9\n\t"
+        "sbbq %[q2], %%r10\n\t"
+        "sbbq %[q3], %%r11\n\t"
+        "cmovcq %%r12, %%r8\n\t"
+        "cmovcq %%r13, %%r9\n\t"
+        "cmovcq %%r14, %%r10\n\t"
+        "cmovcq %%r15, %%r11\n\t"
+        "movq %%r8, 0(%[acc])\n\t"
+        "movq %%r9, 8(%[acc])\n\t"
+        "movq %%r10, 16(%[acc])\n\t"
+        "movq %%r11, 24(%[acc])\n\t"
+        :
+        : [acc] "r"(acc.l), [m] "r"(m), [s] "r"(s), [q0] "m"(FR_MOD.l[0]), [q1] "m"(FR_MOD.l[1]), [q2] "m"(FR_MOD.l[2]),
+          [q3] "m"(FR_MOD.l[3]), [inv] "m"(FR_INV), [zero] "m"(FR_ZERO_WORD)
+        : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+    Fr o = {{acc.l[0], acc.l[1], acc.l[2], acc.l[3]}};
     return o;
 }
 inline bool cpu_has_adx() {
@@ -665,6 +1157,9 @@ inline void poseidon_mds(Fr s[POSEIDON_T], const uint64_t (*m)[4]) {
     for (int i = 0; i < POSEIDON_T; i++) n[i] = dot5(m, (size_t)i * POSEIDON_T, s);
     for (int i = 0; i < POSEIDON_T; i++) s[i] = n[i];
 }
+// (switch for the micro-benchmark only: whether the partial rounds issue the four state[0]-independent products before
+// the S-box chain -- see dot4_acc_adx)
+inline bool& poseidon_split_partial() { static bool on = true; return on; }
 inline void poseidon_permute(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2;
     for (int r = 0; r < half; r++) {
@@ -672,13 +1167,25 @@ inline void poseidon_permute(Fr s[POSEIDON_T]) {
         poseidon_mds(s, POSEIDON_MDS);
     }
     for (int r = 0; r < POSEIDON_RP; r++) {
-        s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
         if (r + 1 < POSEIDON_RP) {
             const size_t b = (size_t)r * (2 * T - 1);
+#ifdef ZKFHE_HAVE_DOT5_ADX
+            if (poseidon_split_partial() && cpu_has_adx()) {
+                Acc512 acc;
+                dot4_acc_adx((const Fr*)POSEIDON_SPARSE[b + 1], s + 1, acc);       // <v, s[1..4]>: independent of the S-box below
+                s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
+                const Fr n0 = fma_redc_adx(acc, (const Fr*)POSEIDON_SPARSE[b], s);    // + m00 * s[0], one reduction
+                for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
+                s[0] = n0;
+                continue;
+            }
+#endif
+            s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
             const Fr n0 = dot5(POSEIDON_SPARSE, b, s);
             for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
             s[0] = n0;
         } else {
+            s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
             poseidon_mds(s, POSEIDON_M_LAST);
         }
     }
