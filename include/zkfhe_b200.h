@@ -350,8 +350,7 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain);
 int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges);
 
 /* Host arithmetic speed on the calling thread, ns per operation: kind 0 = one Poseidon permutation (the form the
- * transcript runs), 1 = one dependent Fr product, 2 = one plain-form permutation, 3 = the permutation of kind 0
- * with the partial rounds' S-box issued before their dot product (an ordering experiment).  `features` (optional) receives a
+ * transcript runs), 1 = one dependent Fr product, 2 = one plain-form permutation.  `features` (optional) receives a
  * short description of the code path (BMI2 / ADX product or the portable one). */
 int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap);
 

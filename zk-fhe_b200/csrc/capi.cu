@@ -181,18 +181,13 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain) {
 }
 
 // ns per operation on the calling host thread: kind 0 = Poseidon permutation (optimised form), 1 = dependent Fr
-// products, 2 = plain-form permutation, 3 = optimised form without the split dot product of the partial rounds.  `features` (optional, >= 64 bytes) says which product the host code runs.
+// products, 2 = plain-form permutation.  `features` (optional, >= 64 bytes) says which product the host code runs.
 int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap) {
-    if (!ns_per_op || !iters || kind < 0 || kind > 3) return ZKFHE_ERR_ARG;
+    if (!ns_per_op || !iters || kind < 0 || kind > 2) return ZKFHE_ERR_ARG;
     host::Fr s[POSEIDON_T];
     for (int i = 0; i < POSEIDON_T; i++) s[i] = host::from_u64(i + 1);
     const auto t0 = std::chrono::steady_clock::now();
     if (kind == 0) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute(s);
-    else if (kind == 3) {                 // the same permutation with the S-box of the partial rounds issued first
-        host::poseidon_split_partial() = false;
-        for (uint32_t i = 0; i < iters; i++) host::poseidon_permute(s);
-        host::poseidon_split_partial() = true;
-    }
     else if (kind == 2) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute_plain(s);
     else for (uint32_t i = 0; i < iters; i++) s[0] = host::mul(s[0], s[1]);
     *ns_per_op = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / iters;

@@ -3,7 +3,9 @@
 // commitments into challenges and a few hundred scalar operations of the opening argument;
 // everything proportional to the domain size runs on the GPU.
 #pragma once
+#include <sched.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "poseidon_consts.h"
@@ -604,498 +606,6 @@ inline Fr dot5_adx(const Fr* m, const Fr* s) {
         : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
     return o;
 }
-// The two halves of a lazily reduced dot product, for the partial rounds: `dot4_acc_adx` accumulates the four products
-// that do not involve state[0] (512 bits, unreduced) and can therefore be issued BEFORE the S-box chain on state[0]
-// in program order; `fma_redc_adx` adds m * s to that accumulator and reduces once.  The out-of-order core then runs
-// the three dependent products of the S-box underneath the four independent ones.
-struct Acc512 { uint64_t l[8]; };
-inline void dot4_acc_adx(const Fr* m, const Fr* s, Acc512& out) {
-    __asm__ volatile(
-        "xorl %%r8d, %%r8d\n\t"
-        "xorl %%r9d, %%r9d\n\t"
-        "xorl %%r10d, %%r10d\n\t"
-        "xorl %%r11d, %%r11d\n\t"
-        "xorl %%r12d, %%r12d\n\t"
-        "xorl %%r13d, %%r13d\n\t"
-        "xorl %%r14d, %%r14d\n\t"
-        "xorl %%r15d, %%r15d\n\t"
-        "movq 0(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 8(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 16(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 24(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 32(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 40(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 48(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 56(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 32(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 40(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 48(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq 56(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 64(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 72(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 80(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 88(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 64(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 72(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 80(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq 88(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 96(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 104(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 112(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 120(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 96(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 104(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 112(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq 120(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r8, 0(%[o])\n\t"
-        "movq %%r9, 8(%[o])\n\t"
-        "movq %%r10, 16(%[o])\n\t"
-        "movq %%r11, 24(%[o])\n\t"
-        "movq %%r12, 32(%[o])\n\t"
-        "movq %%r13, 40(%[o])\n\t"
-        "movq %%r14, 48(%[o])\n\t"
-        "movq %%r15, 56(%[o])\n\t"
-        :
-        : [m] "r"(m), [s] "r"(s), [o] "r"(out.l), [zero] "m"(FR_ZERO_WORD)
-        : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
-}
-inline Fr fma_redc_adx(Acc512& acc, const Fr* m, const Fr* s) {        // the reduced sum lands in acc.l[0..3]
-    __asm__ volatile(
-        "movq 0(%[acc]), %%r8\n\t"
-        "movq 8(%[acc]), %%r9\n\t"
-        "movq 16(%[acc]), %%r10\n\t"
-        "movq 24(%[acc]), %%r11\n\t"
-        "movq 32(%[acc]), %%r12\n\t"
-        "movq 40(%[acc]), %%r13\n\t"
-        "movq 48(%[acc]), %%r14\n\t"
-        "movq 56(%[acc]), %%r15\n\t"
-        "movq 0(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 8(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 16(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq 24(%[s]), %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq 0(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq 8(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq 16(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq 24(%[m]), %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r8, %%rdx\n\t imulq %[inv], %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq %[q0], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r8\n\t"
-        "adcxq %%rbx, %%r9\n\t"
-        "mulxq %[q1], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq %[q2], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq %[q3], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "adoxq %[zero], %%r12\n\t"
-        "adcxq %[zero], %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r9, %%rdx\n\t imulq %[inv], %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq %[q0], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r9\n\t"
-        "adcxq %%rbx, %%r10\n\t"
-        "mulxq %[q1], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq %[q2], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq %[q3], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "adoxq %[zero], %%r13\n\t"
-        "adcxq %[zero], %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r10, %%rdx\n\t imulq %[inv], %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq %[q0], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r10\n\t"
-        "adcxq %%rbx, %%r11\n\t"
-        "mulxq %[q1], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq %[q2], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq %[q3], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "adoxq %[zero], %%r14\n\t"
-        "adcxq %[zero], %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r11, %%rdx\n\t imulq %[inv], %%rdx\n\t"
-        "xorl %%eax, %%eax\n\t"
-        "mulxq %[q0], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r11\n\t"
-        "adcxq %%rbx, %%r12\n\t"
-        "mulxq %[q1], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r12\n\t"
-        "adcxq %%rbx, %%r13\n\t"
-        "mulxq %[q2], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r13\n\t"
-        "adcxq %%rbx, %%r14\n\t"
-        "mulxq %[q3], %%rax, %%rbx\n\t"
-        "adoxq %%rax, %%r14\n\t"
-        "adcxq %%rbx, %%r15\n\t"
-        "adoxq %[zero], %%r15\n\t"
-        "movq %%r12, %%r8\n\t"
-        "movq %%r13, %%r9\n\t"
-        "movq %%r14, %%r10\n\t"
-        "movq %%r15, %%r11\n\t"
-        "subq %[q0], %%r8\n\t"
-        "sbbq %[q1], %%r9\n\t"
-        "sbbq %[q2], %%r10\n\t"
-        "sbbq %[q3], %%r11\n\t"
-        "cmovcq %%r12, %%r8\n\t"
-        "cmovcq %%r13, %%r9\n\t"
-        "cmovcq %%r14, %%r10\n\t"
-        "cmovcq %%r15, %%r11\n\t"
-        "movq %%r8, 0(%[acc])\n\t"
-        "movq %%r9, 8(%[acc])\n\t"
-        "movq %%r10, 16(%[acc])\n\t"
-        "movq %%r11, 24(%[acc])\n\t"
-        :
-        : [acc] "r"(acc.l), [m] "r"(m), [s] "r"(s), [q0] "m"(FR_MOD.l[0]), [q1] "m"(FR_MOD.l[1]), [q2] "m"(FR_MOD.l[2]),
-          [q3] "m"(FR_MOD.l[3]), [inv] "m"(FR_INV), [zero] "m"(FR_ZERO_WORD)
-        : "rax", "rbx", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
-    Fr o = {{acc.l[0], acc.l[1], acc.l[2], acc.l[3]}};
-    return o;
-}
 inline bool cpu_has_adx() {
     static const bool ok = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx");
     return ok;
@@ -1157,9 +667,8 @@ inline void poseidon_mds(Fr s[POSEIDON_T], const uint64_t (*m)[4]) {
     for (int i = 0; i < POSEIDON_T; i++) n[i] = dot5(m, (size_t)i * POSEIDON_T, s);
     for (int i = 0; i < POSEIDON_T; i++) s[i] = n[i];
 }
-// (switch for the micro-benchmark only: whether the partial rounds issue the four state[0]-independent products before
-// the S-box chain -- see dot4_acc_adx)
-inline bool& poseidon_split_partial() { static bool on = true; return on; }
+// (measured on the B200 box's host and not kept: issuing the four state[0]-independent products of a partial round's dot
+// product before the S-box chain, so that the out-of-order core overlaps them -- 16.3 us either way)
 inline void poseidon_permute(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2;
     for (int r = 0; r < half; r++) {
@@ -1169,17 +678,6 @@ inline void poseidon_permute(Fr s[POSEIDON_T]) {
     for (int r = 0; r < POSEIDON_RP; r++) {
         if (r + 1 < POSEIDON_RP) {
             const size_t b = (size_t)r * (2 * T - 1);
-#ifdef ZKFHE_HAVE_DOT5_ADX
-            if (poseidon_split_partial() && cpu_has_adx()) {
-                Acc512 acc;
-                dot4_acc_adx((const Fr*)POSEIDON_SPARSE[b + 1], s + 1, acc);       // <v, s[1..4]>: independent of the S-box below
-                s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
-                const Fr n0 = fma_redc_adx(acc, (const Fr*)POSEIDON_SPARSE[b], s);    // + m00 * s[0], one reduction
-                for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
-                s[0] = n0;
-                continue;
-            }
-#endif
             s[0] = pow5(add(s[0], pc(POSEIDON_K, r)));
             const Fr n0 = dot5(POSEIDON_SPARSE, b, s);
             for (int j = 1; j < T; j++) s[j] = add(s[j], mul(pc(POSEIDON_SPARSE, b + T - 1 + j), s[0]));
@@ -1351,9 +849,16 @@ struct Transcript {
         if (kind == TRANSCRIPT_POSEIDON) {
             buf.push_back(FR_ONE);
             while (buf.size() % 4) buf.push_back(FR_ZERO);
+            // A long absorb (the 5,121 instances: ~1,300 permutations, ~20 ms) is a compute-bound stretch on a host
+            // thread; with many proofs in flight the other proofs' threads need the cores for microseconds at a time to
+            // launch kernels.  Offering the core every ~0.5 ms keeps their wake-up latency (and the GPU's idle gaps)
+            // short; it costs a system call per 32 permutations.  ZKFHE_TRANSCRIPT_YIELD=0 switches it off.
+            static const bool yield_on = [] { const char* e = getenv("ZKFHE_TRANSCRIPT_YIELD"); return !e || atoi(e) != 0; }();
+            const bool long_absorb = yield_on && buf.size() > 512;
             for (size_t i = 0; i < buf.size(); i += 4) {
                 for (int j = 0; j < 4; j++) state[1 + j] = add(state[1 + j], buf[i + j]);
                 poseidon_permute(state);
+                if (long_absorb && (i & 127) == 124) sched_yield();
             }
             buf.clear();
             return state[1];
