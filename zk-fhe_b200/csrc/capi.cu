@@ -265,6 +265,8 @@ void zkfhe_destroy(zkfhe_ctx* ctx) {
     for (auto& kv : ctx->ws) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -289,6 +291,7 @@ int zkfhe_set_blocking_sync(zkfhe_ctx* ctx, int on) {
 int zkfhe_sync(zkfhe_ctx* ctx) {
     if (!ctx) return ZKFHE_ERR_ARG;
     ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+    ctx->h_stage_used = 0;                   // the stream is empty: every staged upload has been consumed
     return ZKFHE_OK;
 }
 

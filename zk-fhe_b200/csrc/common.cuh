@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -75,6 +76,14 @@ struct zkfhe_ctx {
     // core per waiting thread); zkfhe_set_blocking_sync(ctx, 0) switches back to the spinning wait for lowest latency
     bool blocking_sync = true;
     cudaEvent_t sync_event = nullptr;
+    // page-locked landing buffer for the small device -> host read-backs of a proof (commitments, evaluations, status):
+    // a copy into PAGEABLE memory makes cudaMemcpyAsync itself wait -- spinning -- for everything queued before it
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    // ... and a page-locked arena the small host -> device uploads are staged in (a copy FROM pageable memory drains the
+    // stream before it starts); bump-allocated, rewound whenever the stream is known to be empty
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_used = 0;
 };
 enum { ZK_CAT_MSM_ACCUMULATE = 0, ZK_CAT_NTT = 1, ZK_CAT_MSM_OTHER = 2, ZK_CAT_MSM_FOLD = 3, ZK_CAT_MSM_FINAL = 4,
        ZK_CAT_MSM_REFS = 5 /* no time: units = point additions issued by the accumulate kernel */, 
@@ -145,6 +154,54 @@ inline int timed_begin(zkfhe_ctx* ctx, int cat = 0, uint64_t units = 0) {
 inline int timed_end(zkfhe_ctx* ctx) {
     ZK_CUDA(ctx, cudaEventRecord(ctx->ev_pairs[ctx->ev_used].second, ctx->stream));
     ctx->ev_used++;
+    return ZKFHE_OK;
+}
+
+// Page-locked host scratch of at least `bytes` (grow-only; contents are only valid until the next call).
+inline int pinned_get(zkfhe_ctx* ctx, size_t bytes, void** out) {
+    if (ctx->h_pinned_bytes < bytes) {
+        if (ctx->h_pinned) {
+            ZK_CUDA(ctx, stream_wait(ctx));
+            ZK_CUDA(ctx, cudaFreeHost(ctx->h_pinned));
+            ctx->h_pinned = nullptr;
+            ctx->h_pinned_bytes = 0;
+        }
+        const size_t want = bytes < (1u << 16) ? (1u << 16) : bytes + bytes / 4;
+        ZK_CUDA(ctx, cudaHostAlloc(&ctx->h_pinned, want, cudaHostAllocDefault));
+        ctx->h_pinned_bytes = want;
+    }
+    *out = ctx->h_pinned;
+    return ZKFHE_OK;
+}
+// device -> host through the page-locked scratch, then one (sleeping) wait; `h_dst` may be pageable
+inline int read_back(zkfhe_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    void* pin;
+    ZK_TRY(pinned_get(ctx, bytes, &pin));
+    ZK_CUDA(ctx, cudaMemcpyAsync(pin, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, stream_wait(ctx));
+    ctx->h_stage_used = 0;                      // the stream is empty: every staged upload has been consumed
+    memcpy(h_dst, pin, bytes);
+    return ZKFHE_OK;
+}
+// host -> device, asynchronous, from pageable memory: staged through the page-locked arena (uploads larger than a
+// quarter of the arena go straight through cudaMemcpyAsync, which then synchronises by itself)
+static constexpr size_t H_STAGE_BYTES = 4u << 20;
+inline int upload_async(zkfhe_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (!bytes) return ZKFHE_OK;
+    if (bytes > H_STAGE_BYTES / 4) {
+        ZK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return ZKFHE_OK;
+    }
+    if (!ctx->h_stage) ZK_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_stage, H_STAGE_BYTES, cudaHostAllocDefault));
+    const size_t need = (bytes + 63) & ~(size_t)63;
+    if (ctx->h_stage_used + need > H_STAGE_BYTES) {
+        ZK_CUDA(ctx, stream_wait(ctx));
+        ctx->h_stage_used = 0;
+    }
+    uint8_t* slot = ctx->h_stage + ctx->h_stage_used;
+    ctx->h_stage_used += need;
+    memcpy(slot, h_src, bytes);
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return ZKFHE_OK;
 }
 

@@ -615,8 +615,7 @@ static int commit_and_write(zkfhe_prover* pr, const fr_t* d_cols, uint32_t count
     ZK_TRY(comm_allgather(ctx, d_pts, (size_t)per * sizeof(g1_affine)));
     ZK_TRY(points_to_canonical(ctx, d_pts, count));
     std::vector<std::array<uint64_t, 8>> h(count);
-    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pts, (size_t)count * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+    ZK_TRY(read_back(ctx, h.data(), d_pts, (size_t)count * 64));
     for (auto& p : h) pr->tr.write_point(p.data(), p.data() + 4);
     return ZKFHE_OK;
 }
@@ -637,7 +636,7 @@ static int fill_advice(zkfhe_prover* pr, zkfhe_witness* w, uint32_t first_col, c
     const uint32_t nb = pk->n - pk->usable, count = (uint32_t)src.size();
     ColSrc* d_src;
     ZK_TRY(ws_get(ctx, "pr_colsrc", src.size() * sizeof(ColSrc), (void**)&d_src));
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_src, src.data(), src.size() * sizeof(ColSrc), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(upload_async(ctx, d_src, src.data(), src.size() * sizeof(ColSrc)));
     ZK_TRY(fill_random(pr, 0, count * nb));
     dim3 grid((pk->n + 255) / 256, count);
     k_fill_columns<<<grid, 256, 0, ctx->stream>>>(pr->P + (size_t)first_col * pk->n, d_src, pk->n, pk->usable, pr->blind);
@@ -724,15 +723,13 @@ int zkfhe_prove_phase0(zkfhe_prover* pr, zkfhe_witness* w, uint8_t* h_gamma_out)
     uint8_t* d_tmp;
     const size_t ids_bytes = pk->public_cells.size() * 8;
     ZK_TRY(ws_get(ctx, "pr_inst_ids", 64 + ids_bytes + 8, (void**)&d_tmp));
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_tmp, bases, sizeof bases, cudaMemcpyHostToDevice, ctx->stream));
-    if (ids_bytes) ZK_CUDA(ctx, cudaMemcpyAsync(d_tmp + 64, pk->public_cells.data(), ids_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(upload_async(ctx, d_tmp, bases, sizeof bases));
+    if (ids_bytes) ZK_TRY(upload_async(ctx, d_tmp + 64, pk->public_cells.data(), ids_bytes));
     k_fill_instance<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pr->inst, n, (const fr_t* const*)d_tmp, (const uint64_t*)(d_tmp + 64),
                                                              (uint32_t)pk->instances);
     ZK_CHECK_LAUNCH(ctx);
     std::vector<Fr> h_inst(pk->instances);
-    if (pk->instances)
-        ZK_CUDA(ctx, cudaMemcpyAsync(h_inst.data(), pr->inst, pk->instances * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+    if (pk->instances) ZK_TRY(read_back(ctx, h_inst.data(), pr->inst, pk->instances * 32));
     pr->tr.common_scalar(pk->vk_digest);
     for (auto& v : h_inst) pr->tr.common_scalar(v);
     // phase-0 advice columns
@@ -801,8 +798,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(commit_and_write(pr, pr->P + (size_t)pr->ap_base * n, 2 * pk->n_lookup, 1, 1));
         uint32_t st = 0;
-        ZK_CUDA(ctx, cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+        ZK_TRY(read_back(ctx, &st, status, 4));
         if (st & (1u << 6)) {
             k_status_clear_bits<<<1, 1, 0, ctx->stream>>>(status, 1u << 6);      // other recorded asserts stay for zkfhe_status
             ZK_CHECK_LAUNCH(ctx);
@@ -887,7 +883,7 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ypow[0] = host::FR_ONE;
         for (uint32_t i = 1; i < NE; i++) ypow[i] = host::mul(ypow[i - 1], pr->y);
         fr_t* d_ypow = pr->misc + 2 * (size_t)n4;
-        ZK_CUDA(ctx, cudaMemcpyAsync(d_ypow, ypow.data(), (size_t)NE * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_TRY(upload_async(ctx, d_ypow, ypow.data(), (size_t)NE * 32));
         QArgs q{};
         q.E = pr->E; q.F = pk->fixed_ext; q.inst_ext = pr->inst_ext; q.tw_ext = dom4->tw_fwd; q.ypow = d_ypow;
         q.delta_pow = pk->delta_pow; q.f_stride = n4; q.n4 = n4; q.rot = 1u << EXT_SHIFT; q.f_rs = 1; q.f_ro = 0;
@@ -989,14 +985,13 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         ZK_TRY(ws_get(ctx, "pr_evals", sh.G * max_t * 32, (void**)&d_out));
         for (uint32_t v = sh.first; v < sh.last; v++) {
             if (tasks[v].empty()) continue;
-            ZK_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks[v].data(), tasks[v].size() * sizeof(EvalTask), cudaMemcpyHostToDevice, ctx->stream));
+            ZK_TRY(upload_async(ctx, d_tasks, tasks[v].data(), tasks[v].size() * sizeof(EvalTask)));
             k_eval<<<(uint32_t)tasks[v].size(), 256, 0, ctx->stream>>>(d_tasks, pw, n, d_out + (size_t)v * max_t);
             ZK_CHECK_LAUNCH(ctx);
         }
         ZK_TRY(comm_allgather(ctx, d_out, max_t * 32));
         std::vector<Fr> flat(sh.G * max_t);
-        ZK_CUDA(ctx, cudaMemcpyAsync(flat.data(), d_out, flat.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+        ZK_TRY(read_back(ctx, flat.data(), d_out, flat.size() * 32));
         std::vector<size_t> next(sh.G, 0);
         size_t ei = 0;
         for (auto& p : polys)
@@ -1088,8 +1083,8 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
                     ZK_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)n * 32, ctx->stream));
                     continue;
                 }
-                ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs + off, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-                ZK_CUDA(ctx, cudaMemcpyAsync(d_coef + off, set_coef[s][sv].data(), lp.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+                ZK_TRY(upload_async(ctx, d_ptrs + off, lp.data(), lp.size() * 8));
+                ZK_TRY(upload_async(ctx, d_coef + off, set_coef[s][sv].data(), lp.size() * 32));
                 k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs + off, d_coef + off, (uint32_t)lp.size(), n, dst);
                 ZK_CHECK_LAUNCH(ctx);
                 off += lp.size();
@@ -1128,8 +1123,8 @@ int zkfhe_prove_finish(zkfhe_prover* pr, zkfhe_witness* w, uint8_t** proof_out, 
         }
         lp.push_back(acc);
         lc.push_back(host::neg(zt));
-        ZK_CUDA(ctx, cudaMemcpyAsync(d_ptrs, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        ZK_CUDA(ctx, cudaMemcpyAsync(d_coef, lc.data(), lc.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_TRY(upload_async(ctx, d_ptrs, lp.data(), lp.size() * 8));
+        ZK_TRY(upload_async(ctx, d_coef, lc.data(), lc.size() * 32));
         k_lincomb<<<(n + 31) / 32, dim3(32, LC_SPLIT), 0, ctx->stream>>>(d_ptrs, d_coef, (uint32_t)lp.size(), n, Lp);
         ZK_CHECK_LAUNCH(ctx);
         k_sub_const0<<<1, 1, 0, ctx->stream>>>(Lp, dev(cst));

@@ -16,6 +16,7 @@
 #include <vector>
 #include "common.cuh"
 #include "witness.cuh"
+#include "host_ff.h"
 
 using namespace zkfhe;
 
@@ -492,8 +493,7 @@ int zkfhe_status(zkfhe_ctx* ctx) {
     uint32_t* status;
     ZK_TRY(status_word(ctx, &status));
     uint32_t h = 0;
-    ZK_CUDA(ctx, cudaMemcpyAsync(&h, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+    ZK_TRY(read_back(ctx, &h, status, 4));
     h &= 0xffffu;
     if (h == 0) return ZKFHE_OK;
     ZK_CUDA(ctx, cudaMemsetAsync(status, 0, 4, ctx->stream));
@@ -509,12 +509,12 @@ int zkfhe_poly_from_u64(zkfhe_ctx* ctx, const uint64_t* h_coeffs, uint32_t len, 
     ZK_TRY(status_word(ctx, &status));
     void* stage;
     ZK_TRY(ws_get(ctx, "poly_stage", (size_t)len * 8, &stage));
-    ZK_CUDA(ctx, cudaMemcpyAsync(stage, h_coeffs, (size_t)len * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // through the page-locked arena: no stream drain per upload (nine uploads open every proof), and the device-side
+    // staging buffer is only reused by the NEXT call's copy, which the stream orders after this call's kernel
+    ZK_TRY(upload_async(ctx, stage, h_coeffs, (size_t)len * 8));
     ZK_TRY(poly_alloc(ctx, len, bitlen64(modulus), out));
     k_poly_from_u64<<<blocks_for(len), 128, 0, ctx->stream>>>((const uint64_t*)stage, (*out)->d, len, modulus, status);
     ZK_CHECK_LAUNCH(ctx);
-    // the staging buffer is reused by the next call: make the copy-in safe against host reuse too
-    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
     return ZKFHE_OK;
 }
 
@@ -771,7 +771,7 @@ int zkfhe_witness_mock(zkfhe_witness* w, uint64_t* n_violations, uint64_t* first
     unsigned long long* d_out;
     ZK_TRY(ws_get(ctx, "mock_out", 16, (void**)&d_out));
     unsigned long long init[2] = {0, ~0ull};
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_out, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(upload_async(ctx, d_out, init, 16));
     MockBases B{{w->adv[0].p, w->adv[1].p, w->adv[2].p}};
     for (uint32_t c = 0; c < 3; c++) {
         const uint64_t n = w->adv[c].size;
@@ -927,16 +927,15 @@ int zkfhe_chip_reduce_by_modulo(zkfhe_witness* w, uint32_t ctx_gate, const zkfhe
     bound_pow2_div(nbits, modulus, bound, &bound_bits);
     CellCount c1 = cc_check_less_than_safe(bound_bits, lb), c2 = cc_check_less_than_safe(bitlen64(modulus), lb);
     CellCount per{4 + c1.cells + c2.cells, c1.lookups + c2.lookups};
-    // bound -> Montgomery on the device (one thread), passed by value afterwards
-    fr_t* d_bound;
-    ZK_TRY(ws_get(ctx, "bound", sizeof(fr_t), (void**)&d_bound));
+    // bound -> Montgomery on the host, passed to the kernel by value (this used to be a one-thread kernel and a
+    // synchronising read-back per call: six stream drains per proof in the middle of the witness launches)
     fr_t hb;
-    memcpy(hb.v, bound, 32);
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_bound, &hb, 32, cudaMemcpyHostToDevice, ctx->stream));
-    k_to_mont_one<<<1, 1, 0, ctx->stream>>>(d_bound);
-    ZK_CHECK_LAUNCH(ctx);
-    ZK_CUDA(ctx, cudaMemcpyAsync(&hb, d_bound, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(ctx, zkfhe::stream_wait(ctx));
+    {
+        host::Fr c;
+        memcpy(c.l, bound, 32);
+        const host::Fr m = host::to_mont(c);
+        memcpy(hb.v, m.l, 32);
+    }
     OutSpan o;
     uint64_t base;
     ZK_TRY(chip_out(w, ctx_gate, a->len, per, &o, &base));
