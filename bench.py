@@ -461,8 +461,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # single-proof latency and per-kernel device times: one stream alone, CUDA events inside the library
     lat_steps = 5
+    ctx.set_blocking_sync(False)         # a lone proof waits spinning: sleeping costs ~0.3 ms per wake-up, ~4 ms per proof
     ctx.timing_reset()
     lat_ms = timed(lat_steps, True, streams[:1]) / lat_steps
+    ctx.set_blocking_sync(not args.spin)
     acc_ms, acc_spans, acc_pairs = ctx.timing(0)
     ntt_ms, ntt_spans, ntt_elems = ctx.timing(1)
     red_ms = ctx.timing(2)[0] + ctx.timing(3)[0] + ctx.timing(4)[0]

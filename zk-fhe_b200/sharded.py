@@ -26,6 +26,7 @@ def run(k, proofs, transcript, dist, rank, world, local_rank):
     else:
         raise SystemExit("--k must be 13 (config 1) or 16 (the shape of configs 3/4)")
     ctx = capi.Context(local_rank)
+    ctx.set_blocking_sync(False)               # single-proof latency: spinning waits
     ctx.srs_setup(k, TAU)
     zeros = {key: ["0"] * (params.N + 1 if key == "cyclo" else params.N) for key in bfv.INPUT_KEYS}
     kg = bfv.BfvCircuit(ctx, params, record=True)
