@@ -45,9 +45,12 @@ NTT_BYTES_PER_ELEM = 64          # 32 B read + 32 B write
 
 def _traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    command (profiles/r01_traffic.json, written by tools/ncu_traffic.py); {} if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    command (profiles/r02_traffic.json, written by tools/ncu_traffic.py; the round-1 file as a fallback); {} if absent."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return {}
 
 
 TRAFFIC = _traffic()

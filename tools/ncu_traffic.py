@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""profiles/r01_traffic.json from an `ncu --set full` capture of bench.py's dominant kernel.
+"""profiles/r02_traffic.json from an `ncu --set full` capture of bench.py's dominant kernel.
 
-    ncu --set full --clock-control none -k regex:k_msm_accumulate --launch-skip 21 -c 7 -o gpurun_out/bench_acc \\
+    ncu --set full --clock-control none -k regex:k_msm_accumulate --launch-skip <launches of setup + warm-up> -c 7 -o gpurun_out/bench_acc \\
         python bench.py --streams 1 --steps 2 --warmup 3 --no-cpu-baseline
     ncu -i gpurun_out/bench_acc.ncu-rep --page raw --csv > gpurun_out/bench_acc_raw.csv
     python tools/ncu_traffic.py gpurun_out/bench_acc_raw.csv
@@ -40,7 +40,7 @@ def main(path):
            "source": "ncu --set full --clock-control none, k_msm_accumulate launches of one proof of "
                      "`bench.py --streams 1` (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch); "
                      "raw export under profiles/"}
-    json.dump(out, open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
     print(out)
 
 

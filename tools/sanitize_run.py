@@ -5,7 +5,8 @@
     compute-sanitizer --tool racecheck python tools/sanitize_run.py
 
 Field self test, NTT (forward / inverse / coset / coeff_to_extended), MSM (both tables, cluster and single-CTA sort,
-skewed columns), stage (1) + keygen + prove + verify of a small BFV circuit (N = 16, k = 10) with both transcripts,
+skewed columns and runs of equal scalars), stage (1) + keygen + prove + verify of a small BFV circuit (N = 16, k = 10)
+with both transcripts, the same proof as three virtual shards,
 and -- with --full -- one config-1 proof (N = 1024, k = 13).  Results are checked by the product verifier, so a run
 that sanitises clean has also produced valid proofs.  SURVEY.md section 5 (race detection / sanitizers)."""
 import os
@@ -57,6 +58,7 @@ def main():
         sc = rng.integers(0, 1 << 60, size=(3 * n, 4), dtype=np.uint64)
         sc[n:2 * n] = 0
         sc[n:2 * n, 0] = rng.integers(0, 3, size=n).astype(np.uint64)            # skewed: three values only
+        sc[2 * n + 100:2 * n + 900] = sc[2 * n + 99]                              # a run of equal scalars (prefix-table path)
         a = ctx.msm_g1(sc, 3, basis=1)
         b = ctx.msm_g1(sc, 3, basis=0)
         assert len(a) == 192 and len(b) == 192
@@ -79,7 +81,13 @@ def main():
         assert prover.verify(ctx, pk.vk_bytes(), inst, proof, ctx.srs_g2(TAU), transcript=transcript)
     pk2 = prover.import_key(ctx, pk.export_bytes())
     assert pk2.vk_bytes() == pk.vk_bytes()
-    print("small circuit (N=16, k=10): keygen, mock, prove x2, verify x2, pk export/import ok", flush=True)
+    # one proof as three shards (virtual ranks): the sharded commit / grand-product / quotient / opening paths
+    want, _ = prover.prove(pk, lambda: bfv.BfvCircuit(ctx, params), inp, bytes(32), 0)
+    ctx.set_virtual_ranks(3)
+    got, _ = prover.prove(pk, lambda: bfv.BfvCircuit(ctx, params), inp, bytes(32), 0)
+    ctx.set_virtual_ranks(0)
+    assert got == want
+    print("small circuit (N=16, k=10): keygen, mock, prove x2, verify x2, pk export/import, 3-shard proof ok", flush=True)
     if "--full" in sys.argv:
         import json
         ctx.srs_setup(13, TAU)
