@@ -341,8 +341,9 @@ int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t
 
 /* ---- transcript (host arithmetic; callable without a GPU) ----------------------------------
  * The Poseidon permutation behind transcript kind 1 on five Fr elements (Montgomery, 160 bytes, in place):
- * plain = 0 is the optimised form the transcript runs (sparse partial rounds), plain != 0 the textbook form over
- * (round constants, MDS); both return the same state.  Non-canonical input is ZKFHE_ERR_ARG. */
+ * plain = 0 is the form the transcript runs (sparse partial rounds; AVX-512 IFMA where the CPU has it, else scalar),
+ * 1 the textbook form over (round constants, MDS), 2 the scalar optimised form, 3 the IFMA form (ZKFHE_ERR_STATE
+ * without AVX-512 IFMA); all return the same state.  Non-canonical input is ZKFHE_ERR_ARG. */
 int zkfhe_poseidon_permute(uint8_t* state160, int plain);
 /* Replay a message script through a fresh transcript of the given kind: op 1 + 32 bytes = common_scalar (canonical
  * little-endian), op 2 + 64 bytes = common_point (canonical x | y), op 3 = squeeze; the challenges are written to
@@ -350,8 +351,8 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain);
 int zkfhe_transcript_replay(int kind, const uint8_t* script, size_t len, uint8_t* out, size_t cap, size_t* n_challenges);
 
 /* Host arithmetic speed on the calling thread, ns per operation: kind 0 = one Poseidon permutation (the form the
- * transcript runs), 1 = one dependent Fr product, 2 = one plain-form permutation.  `features` (optional) receives a
- * short description of the code path (BMI2 / ADX product or the portable one). */
+ * transcript runs), 1 = one dependent Fr product, 2 = one plain-form permutation, 3 = scalar optimised form, 4 = the
+ * AVX-512 IFMA form.  `features` (optional) receives a short description of the code path. */
 int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap);
 
 /* ---- timing hook -------------------------------------------------------------------------

@@ -95,23 +95,50 @@ def _unmont(v):
     return v * pow(1 << 256, -1, R_MOD) % R_MOD
 
 
-def _permute(lib, state, plain):
+def _permute(lib, state, plain, may_be_unavailable=False):
     buf = bytearray(b"".join(_mont(v).to_bytes(32, "little") for v in state))
     arr = (ctypes.c_char * len(buf)).from_buffer(buf)
-    assert lib.zkfhe_poseidon_permute(ctypes.addressof(arr), plain) == 0
+    rc = lib.zkfhe_poseidon_permute(ctypes.addressof(arr), plain)
+    if may_be_unavailable and rc != 0:
+        return None
+    assert rc == 0
     return [_unmont(int.from_bytes(buf[32 * i:32 * i + 32], "little")) for i in range(5)]
 
 
 def test_host_poseidon_permutation_equals_oracle(lib):
     rnd = random.Random(9)
-    cases = [[0] * 5, [1 << 64, 0, 0, 0, 0], [R_MOD - 1] * 5] + [[rnd.randrange(R_MOD) for _ in range(5)] for _ in range(20)]
+    cases = [[0] * 5, [1 << 64, 0, 0, 0, 0], [R_MOD - 1] * 5, [R_MOD - 1, 0, 1, 2, R_MOD - 2]]
+    cases += [[rnd.randrange(R_MOD) for _ in range(5)] for _ in range(60)]
     for st in cases:
         want = transcript.poseidon_permute(list(st))
         assert _permute(lib, st, 0) == want          # optimised form (what the transcript runs)
         assert _permute(lib, st, 1) == want          # textbook form
+        assert _permute(lib, st, 2) == want          # scalar optimised form (the fallback without AVX-512 IFMA)
+        got = _permute(lib, st, 3, may_be_unavailable=True)       # the AVX-512 IFMA form, where this CPU has it
+        assert got is None or got == want
     bad = bytearray(b"\xff" * 160)
     arr = (ctypes.c_char * 160).from_buffer(bad)
     assert lib.zkfhe_poseidon_permute(ctypes.addressof(arr), 0) != 0       # non-canonical input is refused
+
+
+def test_ifma_permutation_equals_scalar_on_many_states(lib):
+    """The vector form keeps loosely reduced values and a lagged row product (csrc/poseidon_ifma.cpp): hold it
+    against the scalar form on a few thousand states, edge limbs included.  Vacuous without AVX-512 IFMA."""
+    rnd = random.Random(2026)
+    edge = [0, 1, R_MOD - 1, R_MOD - 2, (1 << 52) - 1, 1 << 52, (1 << 104) - 1, (1 << 208) - 1, (1 << 253), R_MOD >> 1]
+
+    def raw(state, form):
+        buf = bytearray(b"".join(v.to_bytes(32, "little") for v in state))       # any canonical value is a valid Montgomery form
+        arr = (ctypes.c_char * len(buf)).from_buffer(buf)
+        return bytes(buf) if lib.zkfhe_poseidon_permute(ctypes.addressof(arr), form) == 0 else None
+
+    for i in range(3000):
+        st = [rnd.choice(edge) if rnd.random() < 0.2 else rnd.randrange(R_MOD) for _ in range(5)]
+        want = raw(st, 2)
+        assert want is not None
+        for form in (0, 3):
+            got = raw(st, form)
+            assert got is None or got == want, (i, form)
 
 
 def _replay(lib, kind, items):

@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzkfhe_b200.so")
 SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "witness.cu", "keygen.cu", "prover.cu", "verifier.cu", "comm.cu"]
+HOST_SOURCES = [("poseidon_ifma.cpp", ["-mavx512f", "-mavx512ifma", "-mavx512vl", "-mbmi2", "-madx"])]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -81,6 +82,20 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
+        with open(obj + ".stamp", "w") as f:
+            f.write(ostamp)
+    # host-only translation units with their own ISA flags (the callers dispatch on cpuid): the AVX-512 IFMA Poseidon
+    for src, flags in HOST_SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(LIBDIR, src.replace(".cpp", ".o"))
+        ostamp = hashlib.sha256(hh.digest() + open(path, "rb").read() + " ".join(flags).encode()).hexdigest()
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == ostamp:
+            continue
+        cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-Wall", *flags, "-c", path, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
         with open(obj + ".stamp", "w") as f:
             f.write(ostamp)
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]

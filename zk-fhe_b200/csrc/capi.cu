@@ -175,26 +175,37 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain) {
     memcpy(s, state160, sizeof s);
     for (auto& v : s)
         if (host::geq(v, host::FR_MOD)) return ZKFHE_ERR_ARG;
-    if (plain) host::poseidon_permute_plain(s); else host::poseidon_permute(s);
+    if (plain == 0) host::poseidon_permute(s);
+    else if (plain == 1) host::poseidon_permute_plain(s);
+    else if (plain == 2) host::poseidon_permute_scalar(s);
+    else if (plain == 3) {
+        if (!host::poseidon_ifma_available()) return ZKFHE_ERR_STATE;
+        host::poseidon_permute_ifma(s);
+    } else return ZKFHE_ERR_ARG;
     memcpy(state160, s, sizeof s);
     return ZKFHE_OK;
 }
 
-// ns per operation on the calling host thread: kind 0 = Poseidon permutation (optimised form), 1 = dependent Fr
-// products, 2 = plain-form permutation.  `features` (optional, >= 64 bytes) says which product the host code runs.
+// ns per operation on the calling host thread: kind 0 = Poseidon permutation (the form the transcript runs), 1 =
+// dependent Fr products, 2 = plain-form permutation, 3 = scalar optimised form, 4 = the AVX-512 IFMA form
+// (poseidon_ifma.cpp).  `features` (optional, >= 64 bytes) says which code path the host runs.
 int zkfhe_host_microbench(int kind, uint32_t iters, double* ns_per_op, char* features, size_t cap) {
-    if (!ns_per_op || !iters || kind < 0 || kind > 2) return ZKFHE_ERR_ARG;
+    if (!ns_per_op || !iters || kind < 0 || kind > 4) return ZKFHE_ERR_ARG;
+    if (kind >= 4 && !host::poseidon_ifma_available()) return ZKFHE_ERR_STATE;
     host::Fr s[POSEIDON_T];
     for (int i = 0; i < POSEIDON_T; i++) s[i] = host::from_u64(i + 1);
     const auto t0 = std::chrono::steady_clock::now();
     if (kind == 0) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute(s);
     else if (kind == 2) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute_plain(s);
+    else if (kind == 3) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute_scalar(s);
+    else if (kind == 4) for (uint32_t i = 0; i < iters; i++) host::poseidon_permute_ifma(s);
     else for (uint32_t i = 0; i < iters; i++) s[0] = host::mul(s[0], s[1]);
     *ns_per_op = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / iters;
     if (s[0].is_zero() && s[1].is_zero()) *ns_per_op = -1;       // keeps the loop observable
     if (features && cap) {
 #if defined(__x86_64__) && defined(__GNUC__)
-        snprintf(features, cap, "%s", host::cpu_has_adx() ? "fr_mul: mulx/adcx/adox" : "fr_mul: portable (no BMI2/ADX)");
+        snprintf(features, cap, "%s%s", host::cpu_has_adx() ? "fr_mul: mulx/adcx/adox" : "fr_mul: portable (no BMI2/ADX)",
+                 host::poseidon_ifma_available() ? "; poseidon: avx512ifma" : "; poseidon: scalar");
 #else
         snprintf(features, cap, "fr_mul: portable");
 #endif

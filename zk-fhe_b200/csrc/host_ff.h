@@ -669,7 +669,7 @@ inline void poseidon_mds(Fr s[POSEIDON_T], const uint64_t (*m)[4]) {
 }
 // (measured on the B200 box's host and not kept: issuing the four state[0]-independent products of a partial round's dot
 // product before the S-box chain, so that the out-of-order core overlaps them -- 16.3 us either way)
-inline void poseidon_permute(Fr s[POSEIDON_T]) {
+inline void poseidon_permute_scalar(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2;
     for (int r = 0; r < half; r++) {
         for (int i = 0; i < T; i++) s[i] = pow5(add(s[i], pc(POSEIDON_C_FIRST, r * T + i)));
@@ -691,6 +691,16 @@ inline void poseidon_permute(Fr s[POSEIDON_T]) {
         for (int i = 0; i < T; i++) s[i] = pow5(add(s[i], pc(POSEIDON_C_SECOND, r * T + i)));
         poseidon_mds(s, POSEIDON_MDS);
     }
+}
+// AVX-512 IFMA form (poseidon_ifma.cpp, compiled separately with the vector flags): the products off the S-box chain
+// run on the vector unit; bit-identical results.  `poseidon_permute` is what the transcript calls.
+void poseidon_permute_ifma(Fr s[POSEIDON_T]);
+bool poseidon_ifma_available();
+inline void poseidon_permute(Fr s[POSEIDON_T]) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (poseidon_ifma_available()) { poseidon_permute_ifma(s); return; }
+#endif
+    poseidon_permute_scalar(s);
 }
 inline void poseidon_permute_plain(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2, rounds = POSEIDON_RF + POSEIDON_RP;
