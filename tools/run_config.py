@@ -4,6 +4,7 @@
     python tools/run_config.py --n 4096 --q 2305843009213693951 --t 65537 --k 16 [--proofs 3]
     python tools/run_config.py --n 4096 --k 16 --rns-bits 109 --limbs 2               # config 3: 109-bit Q as two limb circuits
     python tools/run_config.py --n 16384 --k 19 --rns-bits 438 --limbs 8 [--limb i]   # config 5: 438-bit Q, eight limb circuits
+    torchrun --nproc-per-node 8 tools/run_config.py --ring-degree 16384 --k 19 --rns-bits 438 --limbs 8
         (under torchrun with 8 ranks every rank proves limb RANK on its own GPU: limbs are independent proofs)
 
 Prints the column shape keygen chose, the proving time of each proof (host strings -> proof bytes),
@@ -92,7 +93,7 @@ def run_rns(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--n", "--ring-degree", dest="n", type=int, default=4096, help="N (under torchrun write --ring-degree: torchrun reads a bare --n as one of its own options)")
     ap.add_argument("--q", type=int, default=(1 << 61) - 1)
     ap.add_argument("--t", type=int, default=65537)
     ap.add_argument("--b", type=int, default=19)
