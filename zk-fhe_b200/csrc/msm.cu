@@ -579,6 +579,64 @@ __global__ void __launch_bounds__(32) k_msm_final(uint32_t groups, uint32_t log_
     if (lane == 0) affine_store(out + col, xyzz_to_affine(V));
 }
 
+// Reduction, level 2, CTA-wide: one THREAD per group instead of one lane per groups/32 groups.  The in-lane running
+// sums of k_msm_final (3 * groups/32 dependent point additions before the warp scan even starts) become part of the
+// scan: suffix sums U_g = sum_{m >= g} S_m by a shuffle scan inside each warp plus one shuffle scan of the warp totals,
+// V_g = A_g + fold * [g >= 1] U_g, one shuffle tree per warp and one over the warp results.  ~20 dependent point
+// operations + the inversion instead of ~35, on the same data layout; it is what every commit of a proof ends with
+// (seven times ~250 us at 1.6 % warps active, profiles/r02_ncu_full_bench_reduce.txt).
+__global__ void __launch_bounds__(512) k_msm_final_cta(uint32_t groups, uint32_t log_fold, const g1_xyzz* __restrict__ group_in,
+                                                       g1_affine* out, const uint32_t* __restrict__ bucket_off, uint32_t NB,
+                                                       unsigned long long* refs_total) {
+    __shared__ g1_xyzz sh[16];                                    // one slot per warp (<= 512 threads)
+    const uint32_t col = blockIdx.x, g = threadIdx.x, lane = g & 31, wid = g >> 5, nw = blockDim.x >> 5;
+    if (g == 0) atomicAdd(refs_total, (unsigned long long)bucket_off[(size_t)col * (NB + 1) + NB]);
+    const g1_xyzz* in = group_in + (size_t)col * groups * 2;
+    g1_xyzz S = xyzz_load(in + 2 * (size_t)g);
+    const g1_xyzz A = xyzz_load(in + 2 * (size_t)g + 1);
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {                       // inclusive suffix scan of S inside the warp
+        g1_xyzz v = xyzz_shfl_down(S, d);
+        if (lane + d < 32) xyzz_add_ni(S, v);
+    }
+    if (lane == 0) sh[wid] = S;                                   // this warp's total
+    __syncthreads();
+    if (wid == 0) {                                               // exclusive suffix sums of the warp totals
+        g1_xyzz T = lane < nw ? sh[lane] : xyzz_identity();
+#pragma unroll 1
+        for (uint32_t d = 1; d < nw; d <<= 1) {
+            g1_xyzz v = xyzz_shfl_down(T, d);
+            if (lane + d < nw) xyzz_add_ni(T, v);
+        }
+        // T = sum_{m >= lane}; what warp `lane` must add is sum_{m > lane} = the next lane's inclusive sum
+        g1_xyzz nxt = xyzz_shfl_down(T, 1);
+        if (lane < nw) sh[lane] = lane + 1 < nw ? nxt : xyzz_identity();
+    }
+    __syncthreads();
+    if (wid + 1 < nw) xyzz_add_ni(S, sh[wid]);                    // S = U_g
+    g1_xyzz V = g ? S : xyzz_identity();
+#pragma unroll 1
+    for (uint32_t i = 0; i < log_fold; i++) V = xyzz_dbl_ni(V);
+    xyzz_add_ni(V, A);
+#pragma unroll 1
+    for (uint32_t d = 16; d > 0; d >>= 1) {
+        g1_xyzz v = xyzz_shfl_down(V, d);
+        if (lane < d) xyzz_add_ni(V, v);
+    }
+    __syncthreads();                                              // everyone has read its suffix from sh
+    if (lane == 0) sh[wid] = V;
+    __syncthreads();
+    if (wid == 0) {
+        g1_xyzz W = lane < nw ? sh[lane] : xyzz_identity();
+#pragma unroll 1
+        for (uint32_t d = 16; d > 0; d >>= 1) {
+            g1_xyzz v = xyzz_shfl_down(W, d);
+            if (lane < d) xyzz_add_ni(W, v);
+        }
+        if (lane == 0) affine_store(out + col, xyzz_to_affine(W));
+    }
+}
+
 // ---- test SRS (halo2 `ParamsKZG::setup` shape): g[i] = tau^i G, g_lagrange[i] = l_i(tau) G --------
 __device__ __noinline__ g1_affine g1_generator_mul(const fr_t k_canon) {
     g1_affine g;
@@ -772,15 +830,23 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     // a cluster of 8 CTAs per column when there are few columns or they are long; one CTA per column otherwise
     bool cluster_sort = log_n >= 13 && NB >= 8 * SORT_CS && (batch < 32 || log_n >= 15);
     if (const char* e = getenv("ZKFHE_MSM_CLUSTER_SORT")) cluster_sort = cluster_sort && atoi(e) != 0;
+    // the final reduction as one thread per group (a CTA per column) wherever a column has 64..512 groups
+    bool cta_final = groups >= 64 && groups <= 512 && (groups & (groups - 1)) == 0;
+    if (const char* e = getenv("ZKFHE_MSM_CTA_FINAL")) cta_final = cta_final && atoi(e) != 0;
+    // a column goes through the combine levels when some bucket holds more references than this.  Few-column commits
+    // (16-reference slices, fold lanes walking their own bucket's partial sums) can take 8 slices per bucket before a
+    // combine launch (~90 us on an empty GPU) is cheaper than the extra additions: uniform scalars (~40 +- 20 references
+    // per bucket) then skip it; witness-like columns still exceed it by orders of magnitude.
+    const uint32_t skew_limit = (batch < 32 ? 8 : 3) * SEG;
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
         const fr_t* sc = d_scalars + (uint64_t)done * stride;
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_OTHER, 0));
         if (cluster_sort)
-            k_msm_sort_cluster<<<nb * SORT_CS, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew, ps_base);
+            k_msm_sort_cluster<<<nb * SORT_CS, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, skew_limit, skew, ps_base);
         else
-            k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, 3 * SEG, skew, ps_base);
+            k_msm_sort<<<nb, 1024, smem, ctx->stream>>>(sc, stride, n, c, W, boff, soff, sorted, max_refs, skew_limit, skew, ps_base);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_ACCUMULATE, (uint64_t)nb * n));
@@ -808,7 +874,8 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
         ZK_TRY(timed_begin(ctx, ZK_CAT_MSM_FINAL, 0));
-        k_msm_final<<<nb, 32, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done, boff, NB, refs);
+        if (cta_final) k_msm_final_cta<<<nb, groups, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done, boff, NB, refs);
+        else k_msm_final<<<nb, 32, 0, ctx->stream>>>(groups, log_fold, grp, d_out + done, boff, NB, refs);
         ZK_CHECK_LAUNCH(ctx);
         ZK_TRY(timed_end(ctx));
     }
