@@ -31,7 +31,7 @@ K = 13
 N_ROWS = 1 << K
 K_EXT = 15
 N_POLY, Q_MOD, T_MOD, B_ERR = 1024, 536870909, 7, 19
-TAU = 0x5EED5EED5EED5EED5EED5EED5EED            # insecure test SRS trapdoor (the reference's gen_srs is a test setup too)
+TAU = None          # set in main(): the trapdoor of the reference's own fallback SRS (zkfhe_reference_test_tau), a test setup
 # column counts of one proof (reference circuit shape; permutation chunks of 2 columns at degree 4)
 C_ADVICE = 3 + 153 + 5 + 36
 C_LOOKUP_PERM = 2 * 36
@@ -278,7 +278,8 @@ def cpu_reference_arm(steps, warmup, threads=0, budget_s=240.0):
     sec = float(np.mean(times))
     split = {k: round(float(np.mean([p[k] for p in parts])), 4) for k in first}
     return {"value": 1.0 / sec, "unit": "proofs/s", "cores": int(threads), "kind": "port",
-            "sample": f"{steps} whole CPU passes (after {warm_done} warm-up), each = stage (1) in C (schoolbook products, long division, "
+            "sample": f"{steps} whole CPU passes (after {warm_done} warm-up), each ONE proof (a bounded sample of the GPU arm's step, "
+                      f"which is a batch of proofs; the unit, proofs/s, is the same) = stage (1) in C (schoolbook products, long division, "
                       f"all {23558 + 1231992 + 32764} advice + 286756 lookup cells) + all {C_MSM} MSMs + {C_NTT} iNTT(2^13) + "
                       f"{C_NTT + 1} coset NTT(2^15) + 1 extended iNTT, on the step's real advice / permuted-lookup columns (the 142 "
                       f"grand-product / random / quotient / opening columns are uniform field elements, as in a real proof); grand "
@@ -315,6 +316,9 @@ def main():
     config = {"workload": "bfv_prove_N1024_Q29bit_T7_B19_k13", "N": N_POLY, "Q": Q_MOD, "k": K, "advice_columns": C_ADVICE,
               "instances": 5121, "commitments_per_proof": C_MSM, "ext_k": K_EXT,
               "transcript": "blake2b" if args.transcript == 0 else "poseidon",
+              "proofs_per_step": max(1, args.streams),
+              "step": f"one batch of {max(1, args.streams)} proofs per GPU (one synthetic witness per proof stream); the timed region is "
+                      f"steps x {max(1, args.streams)} proofs per GPU, handed to the streams as they become free",
               "parallelism": f"{args.streams} proofs in flight per GPU (one stream + host thread each) x {max(world, args.gpus)} GPU(s); "
                              f"proofs are independent units, no data-path collective",
               "cache": "per-proof working set (prover polynomials 104 MB + extended 416 MB + fixed extended 383 MB + MSM "
@@ -338,6 +342,8 @@ def main():
 
     import zk_fhe_b200
     from zk_fhe_b200 import bfv, prover
+    global TAU
+    TAU = zk_fhe_b200.reference_test_tau()
 
     if world > 1:
         # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON
@@ -405,6 +411,7 @@ def main():
 
     def run_steps(steps, from_host, workers):
         """Exactly `steps` proofs, handed out dynamically to the proof streams."""
+        steps = int(steps)
         start = counter[0]
         counter[0] += steps
         nxt = [start]
@@ -452,15 +459,18 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    run_steps(max(args.warmup, len(streams)), False, streams)
+    # a step is one batch of len(streams) proofs: with one proof per step the timed region of a 20-step run would be a
+    # single generation of 16 in-flight proofs plus a drain (0.25 s); steps x batch proofs time the steady state
+    batch = len(streams)
+    run_steps(max(args.warmup, 1) * batch, False, streams)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = sum(ps.ctx.launch_count() for ps in streams)
-    total_ms = timed(args.steps, False, streams)
+    total_ms = timed(args.steps * batch, False, streams)
     launches = sum(ps.ctx.launch_count() for ps in streams) - launches0
-    run_steps(min(args.warmup, 2) * len(streams), True, streams)
-    e2e_ms = timed(args.steps, True, streams)
+    run_steps(min(args.warmup, 2) * batch, True, streams)
+    e2e_ms = timed(args.steps * batch, True, streams)
     clocks = sampler.stop() if rank == 0 else None
     # single-proof latency and per-kernel device times: one stream alone, CUDA events inside the library
     lat_steps = 5
@@ -481,7 +491,8 @@ def main():
     if rank == 0:
         peak, peak_kind = peaks()
         ms_per_step = total_ms / args.steps
-        value = world * 1e3 / ms_per_step
+        value = world * batch * 1e3 / ms_per_step
+        config["ms_per_proof"] = ms_per_step / batch
         achieved = MSM_BYTES_PER_PAIR * acc_pairs / (acc_ms * 1e-3) / 1e9
         ntt_ach = NTT_BYTES_PER_ELEM * ntt_elems / (ntt_ms * 1e-3) / 1e9
         in_bytes = sum(len(v) for v in inputs[0].values()) * 8
@@ -490,8 +501,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u256 (BN254 Fr/Fq, 8xu32 Montgomery)",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": world * 1e3 / (e2e_ms / args.steps), "unit": "proofs/s",
-                    "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(proof_len[0]),
+            "e2e": {"value": world * batch * 1e3 / (e2e_ms / args.steps), "unit": "proofs/s",
+                    "h2d_bytes_per_step": int(in_bytes) * batch, "d2h_bytes_per_step": int(proof_len[0]) * batch,
                     "prove_latency_s_single_stream": lat_ms / 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": peak,

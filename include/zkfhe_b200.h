@@ -105,6 +105,12 @@ int zkfhe_load_srs(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_g, const uint8_t
  * GPU from an explicit tau (Fr, Montgomery) and loaded as by zkfhe_load_srs.  The bases are also
  * copied to the host when the output pointers are non-NULL (n x 64 bytes each).  INSECURE. */
 int zkfhe_srs_setup(zkfhe_ctx* ctx, uint32_t k, const uint8_t* h_tau_fr, uint8_t* h_g_out, uint8_t* h_g_lagrange_out);
+/* The tau of the reference's OWN test SRS: halo2-scaffold `gen_srs(k)` without a params file runs
+ * `ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32]))`, whose first draw `Fr::random` is the first 64 ChaCha20
+ * keystream bytes (zero key / counter / nonce: RFC 7539 A.1 #1) as a little-endian 512-bit integer mod r
+ * [UPSTREAM-RECALL].  Writes tau (Fr, Montgomery, 32 bytes) and, when `keystream64` is non-NULL, the 64 keystream
+ * bytes.  Host only; what `bfv --insecure-test-srs` and bench.py feed to zkfhe_srs_setup.  INSECURE by construction. */
+int zkfhe_reference_test_tau(uint8_t* tau_fr32, uint8_t* keystream64);
 /* Make `dst` use the resident commitment-key tables of `src` (same GPU; `src` must outlive `dst`). */
 int zkfhe_share_srs(zkfhe_ctx* dst, const zkfhe_ctx* src);
 /* In place: canonical 256-bit integers -> Montgomery Fr (to_montgomery = 1) or back (0). */

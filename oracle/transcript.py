@@ -136,3 +136,31 @@ class PoseidonTranscript:
 
 def make(kind):
     return PoseidonTranscript() if kind == 1 else Blake2bTranscript()
+
+
+# ---- the reference's fallback SRS trapdoor ------------------------------------------------------------------------
+# halo2-scaffold `gen_srs(k)` without a params file: `ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32]))`; the first
+# draw is tau = `Fr::random(rng)`: eight `next_u64` = the first 64 keystream bytes, little-endian, as one 512-bit integer
+# reduced mod r [UPSTREAM-RECALL, SURVEY.md App. C.1].  Zero key / counter / nonce is RFC 7539 A.1 test vector #1.
+def chacha20_block(key_words, counter=0, stream=0):
+    def rotl(v, n):
+        return ((v << n) | (v >> (32 - n))) & 0xFFFFFFFF
+
+    init = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574, *key_words, counter & 0xFFFFFFFF, counter >> 32,
+            stream & 0xFFFFFFFF, stream >> 32]
+    x = list(init)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = rotl(x[b] ^ x[c], 7)
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return b"".join(((x[i] + init[i]) & 0xFFFFFFFF).to_bytes(4, "little") for i in range(16))
+
+
+def reference_test_tau():
+    return int.from_bytes(chacha20_block([0] * 8), "little") % R_MOD

@@ -195,3 +195,24 @@ def test_poseidon_point_encoding_reduces_coordinates_mod_r(lib):
     t.common_scalar(5)
     t.common_scalar(R_MOD - 1)
     assert got == [t.squeeze()]
+
+
+RFC7539_A1_1 = bytes.fromhex("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+                             "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+
+
+def test_reference_test_srs_trapdoor(lib):
+    """`--insecure-test-srs` / bench.py use the trapdoor of the reference's own fallback SRS (`ParamsKZG::setup` from
+    `ChaCha20Rng::from_seed([0; 32])`): ChaCha20's zero-key block is RFC 7539 appendix A.1 test vector #1, and tau is
+    that block as a little-endian 512-bit integer mod r -- in the oracle and in the library."""
+    assert transcript.chacha20_block([0] * 8) == RFC7539_A1_1
+    tau = int.from_bytes(RFC7539_A1_1, "little") % R_MOD
+    assert transcript.reference_test_tau() == tau
+    out, ks = bytearray(32), bytearray(64)
+    a = (ctypes.c_char * 32).from_buffer(out)
+    b = (ctypes.c_char * 64).from_buffer(ks)
+    assert lib.zkfhe_reference_test_tau(ctypes.addressof(a), ctypes.addressof(b)) == 0
+    assert bytes(ks) == RFC7539_A1_1
+    assert _unmont(int.from_bytes(out, "little")) == tau
+    import zk_fhe_b200
+    assert zk_fhe_b200.reference_test_tau() == tau

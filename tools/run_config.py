@@ -20,7 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-TAU = 0x5EED5EED5EED5EED5EED5EED
+TAU = None          # set below: the trapdoor of the reference's own fallback SRS (zkfhe_reference_test_tau)
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 R_INV = pow(1 << 256, -1, R_MOD)
 
@@ -105,6 +105,9 @@ def main():
     ap.add_argument("--limb", type=int, default=-1, help="RNS mode: prove only this limb (default: all, or limb RANK under torchrun)")
     ap.add_argument("--json", default="", help="write a machine-readable summary here")
     args = ap.parse_args()
+    global TAU
+    import zk_fhe_b200 as _z
+    TAU = _z.reference_test_tau()
     if args.rns_bits:
         return run_rns(args)
     import zk_fhe_b200

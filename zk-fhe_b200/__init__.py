@@ -8,4 +8,4 @@ __path__ points here).
   build    nvcc build of lib/libzkfhe_b200.so for sm_100a
   csrc/    hand-written CUDA: field/curve arithmetic, NTT, MSM, witness kernels
 """
-from .capi import Context, ZkfheError, declared_symbols, load_library  # noqa: F401
+from .capi import Context, ZkfheError, declared_symbols, load_library, reference_test_tau  # noqa: F401

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "zkfhe_pairing_check": (_c.c_int, [_u8p, _u8p, _c.c_uint32, _c.POINTER(_c.c_int)]),
     "zkfhe_pairing": (_c.c_int, [_u8p, _u8p, _c.c_int, _u8p]),
     "zkfhe_srs_g2": (_c.c_int, [_u8p, _u8p]),
+    "zkfhe_reference_test_tau": (_c.c_int, [_u8p, _u8p]),
     "zkfhe_vk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,
                                 _c.POINTER(_c.c_int)]),
@@ -153,6 +154,16 @@ FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 def fr_mont_bytes(x):
     """Canonical int -> the 32-byte ABI layout of an Fr element (Montgomery, R = 2^256)."""
     return bytearray((((int(x) % FR_MODULUS) << 256) % FR_MODULUS).to_bytes(32, "little"))
+
+
+def reference_test_tau():
+    """The trapdoor of the reference's own fallback SRS (halo2-scaffold `gen_srs` without a params file:
+    `ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32]))`), as a canonical int.  INSECURE: tests and benchmarks."""
+    out = bytearray(32)
+    rc = load_library().zkfhe_reference_test_tau(_addr(out), None)
+    if rc != 0:
+        raise ZkfheError(rc, "zkfhe_reference_test_tau failed")
+    return int.from_bytes(out, "little") * pow(1 << 256, -1, FR_MODULUS) % FR_MODULUS
 
 
 def load_library(build_if_missing=True):

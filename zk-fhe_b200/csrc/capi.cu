@@ -186,6 +186,18 @@ int zkfhe_poseidon_permute(uint8_t* state160, int plain) {
     return ZKFHE_OK;
 }
 
+// The trapdoor of the reference's fallback SRS (host_ff.h reference_test_tau) and the ChaCha20 block it comes from.
+int zkfhe_reference_test_tau(uint8_t* tau_fr32, uint8_t* keystream64) {
+    if (!tau_fr32) return ZKFHE_ERR_ARG;
+    const host::Fr t = host::reference_test_tau();
+    memcpy(tau_fr32, t.l, 32);
+    if (keystream64) {
+        const uint32_t zero_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        host::chacha20_block(zero_key, 0, 0, keystream64);
+    }
+    return ZKFHE_OK;
+}
+
 // ns per operation on the calling host thread: kind 0 = Poseidon permutation (the form the transcript runs), 1 =
 // dependent Fr products, 2 = plain-form permutation, 3 = scalar optimised form, 4 = the AVX-512 IFMA form
 // (poseidon_ifma.cpp).  `features` (optional, >= 64 bytes) says which code path the host runs.

@@ -788,6 +788,37 @@ inline Fr from_uniform_bytes(const uint8_t b[64]) {
     return add(mul(d0, FR_R2), mul(d1, FR_R3));
 }
 
+// ---- the reference's own test trapdoor -----------------------------------------------------------
+// halo2-scaffold `gen_srs(k)` without a params file: `ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32]))`, whose
+// first draw is tau = `Fr::random(rng)` = the first 64 keystream bytes (eight `next_u64`, little-endian) as a 512-bit
+// integer reduced mod r [UPSTREAM-RECALL, SURVEY.md App. C.1].  ChaCha20 with an all-zero key, counter and nonce is
+// RFC 7539 appendix A.1 test vector #1, which the CPU tests pin, so this tau (and with it g[i] = tau^i G of the
+// `--insecure-test-srs` commitment key) is a function of published constants only.
+inline void chacha20_block(const uint32_t key[8], uint64_t counter, uint64_t stream, uint8_t out[64]) {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5],
+                       key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t x[16];
+    memcpy(x, in, sizeof x);
+    auto rotl = [](uint32_t v, int n) { return (v << n) | (v >> (32 - n)); };
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    };
+    for (int i = 0; i < 10; i++) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) { const uint32_t v = x[i] + in[i]; memcpy(out + 4 * i, &v, 4); }
+}
+inline Fr reference_test_tau() {                       // Montgomery form
+    const uint32_t zero_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t ks[64];
+    chacha20_block(zero_key, 0, 0, ks);
+    return from_uniform_bytes(ks);
+}
+
 // ---- transcript ------------------------------------------------------------------------------
 // Two interchangeable Fiat-Shamir hashes over the same message sequence:
 //   POSEIDON (default; what the reference's `prove` runs: snark-verifier-sdk `gen_snark_shplonk` ->

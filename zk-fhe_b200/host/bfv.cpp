@@ -13,7 +13,8 @@
 //
 // Commitment key: `--srs <file>` (default params/kzg_bn254_<k>.srs, the path halo2-scaffold's gen_srs reads) holds
 // g, g_lagrange and [tau]_2; `bfv -k <k> setup` writes one from a trapdoor drawn from the OS and then forgotten.
-// Without a file the tool REFUSES to run unless `--insecure-test-srs` is given: that flag uses a fixed public trapdoor
+// Without a file the tool REFUSES to run unless `--insecure-test-srs` is given: that flag uses the public trapdoor of the
+// reference's own fallback (`ParamsKZG::setup` from `ChaCha20Rng` seed 0, zkfhe_reference_test_tau)
 // (anyone can forge proofs against it) and exists for tests and benchmarks only.  The reference falls back to such a
 // test setup silently; this tool makes the caller say so.
 // The proof / pk / vk / snark / srs formats are this implementation's own.
@@ -152,10 +153,11 @@ int main(int argc, char** argv) {
         // the commitment key for keygen / prove (loaded on the device) and [tau]_2 for verify
         auto load_srs = [&](Device* dev) {
             if (insecure_srs) {
-                fprintf(stderr, "WARNING: --insecure-test-srs: the KZG trapdoor is a fixed PUBLIC constant; proofs against this key can be "
-                                "forged by anyone.  Tests and benchmarks only.\n");
+                fprintf(stderr, "WARNING: --insecure-test-srs: the KZG trapdoor is a PUBLIC constant (the reference's own fallback, "
+                                "ParamsKZG::setup from ChaCha20Rng seed 0); proofs against this key can be forged by anyone.  "
+                                "Tests and benchmarks only.\n");
                 uint8_t tau[32];
-                fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau);
+                if (zkfhe_reference_test_tau(tau, nullptr) != ZKFHE_OK) throw Error(ZKFHE_ERR_ARG, "reference_test_tau failed");
                 if (dev) dev->check(zkfhe_srs_setup(dev->raw(), k, tau, nullptr, nullptr));
                 if (zkfhe_srs_g2(tau, s_g2) != ZKFHE_OK) throw Error(ZKFHE_ERR_ARG, "srs_g2 failed");
                 return;
@@ -168,7 +170,7 @@ int main(int argc, char** argv) {
             // halo2 `ParamsKZG::setup` shape from a trapdoor that never leaves this function.  Still a single-party
             // setup: whoever runs it could have kept tau.  Use a ceremony transcript for anything real.
             uint8_t seed[64], tau[32];
-            if (insecure_srs) { fr_mont_from_u64(0x5EED5EED5EED5EEDULL, tau); }
+            if (insecure_srs) { if (zkfhe_reference_test_tau(tau, nullptr) != ZKFHE_OK) throw Error(ZKFHE_ERR_ARG, "reference_test_tau failed"); }
             else {
                 os_random(seed, 64);
                 host::Fr t = host::from_uniform_bytes(seed);

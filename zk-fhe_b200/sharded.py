@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-TAU = 0x5EED5EED5EED5EED5EED5EED
+TAU = None          # run(): the trapdoor of the reference's own fallback SRS (capi.reference_test_tau)
 
 
 def run(k, proofs, transcript, dist, rank, world, local_rank):
@@ -25,6 +25,8 @@ def run(k, proofs, transcript, dist, rank, world, local_rank):
         params = bfv.BfvParams(N=4096, Q=(1 << 61) - 1, T=65537, B=19)
     else:
         raise SystemExit("--k must be 13 (config 1) or 16 (the shape of configs 3/4)")
+    global TAU
+    TAU = capi.reference_test_tau()
     ctx = capi.Context(local_rank)
     ctx.set_blocking_sync(False)               # single-proof latency: spinning waits
     ctx.srs_setup(k, TAU)

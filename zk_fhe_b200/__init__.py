@@ -2,4 +2,4 @@
 import os as _os
 
 __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "zk-fhe_b200"))
-from .capi import Context, ZkfheError, declared_symbols, load_library  # noqa: E402,F401
+from .capi import Context, ZkfheError, declared_symbols, load_library, reference_test_tau  # noqa: E402,F401
