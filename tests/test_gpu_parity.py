@@ -54,6 +54,21 @@ def test_ntt_matches_oracle(ctx, k, inverse, coset):
     assert np.array_equal(data, want)
 
 
+@pytest.mark.parametrize("k,batch", [(8, 1), (8, 32), (10, 2), (10, 8), (10, 9), (11, 1), (11, 4), (11, 5), (7, 3), (12, 1), (13, 1), (13, 6), (13, 9),
+                                     (15, 1), (15, 2), (15, 3), (16, 1), (16, 2), (17, 1)])
+@pytest.mark.parametrize("inverse,coset", [(False, False), (True, True)])
+def test_small_ntt_both_paths(ctx, k, batch, inverse, coset):
+    """Transforms of 2^8..2^11 points take the tiled two-pass path while batch * n <= 8192 (the lone transforms of
+    stage (1)) and the one-CTA path above that; larger ones use 256-element tiles while batch * n <= 65536 and
+    1024-element tiles above: all against the oracle, either side of each switch."""
+    rng = np.random.default_rng(7000 + 31 * k + batch)
+    data = random_fr_mont(rng, batch << k)
+    want = data.copy()
+    cbind.ntt(want, k, batch, inverse=inverse, coset=coset)
+    ctx.ntt_fr(data, k, batch, inverse=inverse, coset=coset)
+    assert np.array_equal(data, want)
+
+
 def test_ntt_edge_inputs(ctx):
     k = 13
     n = 1 << k

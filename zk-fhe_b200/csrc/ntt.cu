@@ -384,7 +384,10 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
     p.zeta2 = fr_t{ZKFHE_FR_ZETA2_MONT};
     timed_call_start(ctx);
     ZK_TRY(timed_begin(ctx, ZK_CAT_NTT, (uint64_t)batch << log_n));
-    if (log_n <= 11) {
+    // A lone small transform (stage (1): two or one 2N-point transforms per Poly::mul) on one CTA is a 90-butterfly
+    // dependent walk per thread (~80 us at 2^11); cut into 128-element tiles it is two launches of 16 one-warp CTAs.
+    const bool small_tiles = log_n >= 8 && log_n <= 11 && ((uint64_t)batch << log_n) <= 8192;
+    if (log_n <= 11 && !small_tiles) {
         p.in = d_in; p.out = d_out; p.in_stride = in_stride; p.out_stride = out_stride;
         p.log_r = log_n; p.log_l = 0; p.mode = 1; p.in_len = in_len;
         p.pre_coset = (!inverse && coset); p.post_scale = inverse; p.post_coset = (inverse && coset);
@@ -396,6 +399,10 @@ int ntt_run(zkfhe_ctx* ctx, const fr_t* d_in, uint64_t in_stride, uint32_t in_le
         if (const char* e = getenv("ZKFHE_NTT_LOG_T")) log_t = (uint32_t)atoi(e);      // tuning knob (tools/bench_kernels.py)
         if (log_t < 10) log_t = 10;
         if (log_t > 12) log_t = 12;
+        if (small_tiles) log_t = 7;
+        // few columns of 2^12 .. 2^16 (the SHPLONK round, single-column transforms): 256-element tiles on one-warp CTAs
+        // put 32+ CTAs on the GPU instead of 8 (25-49 us per launch with 1024-element tiles)
+        else if (((uint64_t)batch << log_n) <= 65536 && !getenv("ZKFHE_NTT_LOG_T")) log_t = 8;
         if (log_t < (log_n + 1) / 2) log_t = (log_n + 1) / 2;          // a tile holds at least one whole pass-A column
         const uint32_t log_ra = (log_n + 1) / 2, log_c = log_n - log_ra;
         fr_t* tmp;
