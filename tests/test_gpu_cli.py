@@ -72,6 +72,11 @@ def test_cli_insecure_test_srs_is_opt_in_and_loud(workdir):
     assert r.returncode == 0 and "WARNING" in r.stderr, r.stderr
     r = _run(workdir, *flags, "verify")
     assert r.returncode == 0 and "Snark verified successfully" in r.stdout, r.stdout + r.stderr
+    # serving shape from C++ host threads: 12 more proofs on 4 proof streams, then the usual .snark (which still verifies)
+    r = _run(workdir, *flags, "--input", "bfv/bfv.in", "--repeat", "12", "--streams", "4", "prove")
+    assert r.returncode == 0 and "Throughput:" in r.stdout and "4 proof streams" in r.stdout, r.stdout + r.stderr
+    r = _run(workdir, *flags, "verify")
+    assert r.returncode == 0 and "Snark verified successfully" in r.stdout, r.stdout + r.stderr
     r = _run(workdir, "verify")                                  # the params file is missing: verify refuses too
     assert r.returncode == 1 and "setup" in r.stderr
     os.remove(workdir / "data" / "bfv.pk")

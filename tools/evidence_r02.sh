@@ -1,5 +1,5 @@
 set -x
-O=gpurun_out/r2p; mkdir -p $O
+O=gpurun_out/r2w; mkdir -p $O
 B="python bench.py --streams 1 --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $O/launches.csv $B > $O/bench_under_ncu.json 2> $O/ncu1.err
 ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate --launch-skip 22 -c 7 -o $O/bench_acc $B > /dev/null 2> $O/ncu2.err
@@ -9,7 +9,7 @@ for f in bench_acc bench_reduce bench_ntt; do ncu -i $O/$f.ncu-rep --page raw --
 rm -f $O/bench_reduce.ncu-rep $O/bench_ntt.ncu-rep
 # CLI flow with timings
 W=$(mktemp -d); mkdir -p $W/data/bfv $W/configs $W/params; cp tests/golden/bfv.in tests/golden/bfv_empty.in $W/data/bfv/
-( cd $W; BIN=$GRAFT_REPO_ROOT/zk-fhe_b200/bin/bfv; for c in "setup" "--input bfv/bfv_empty.in keygen" "--input bfv/bfv.in prove" "verify" "--input bfv/bfv.in --transcript blake2b prove" "verify"; do echo "== bfv --name bfv -k 13 $c"; ( time $BIN --name bfv -k 13 $c ); done ) > $O/cli.txt 2>&1
+( cd $W; BIN=$GRAFT_REPO_ROOT/zk-fhe_b200/bin/bfv; for c in "setup" "--input bfv/bfv_empty.in keygen" "--input bfv/bfv.in prove" "verify" "--input bfv/bfv.in --transcript blake2b prove" "verify"; do echo "== bfv --name bfv -k 13 $c"; ( time $BIN --name bfv -k 13 $c ); done; echo "== bfv prove --repeat 320 --streams 16 (C++ host threads)"; $BIN --name bfv -k 13 --input bfv/bfv.in --repeat 320 --streams 16 prove; $BIN --name bfv -k 13 --input bfv/bfv.in --transcript blake2b --repeat 320 --streams 16 prove ) > $O/cli.txt 2>&1
 # config 5: one limb of the 438-bit RNS modulus at N = 16384, k = 19
 python tools/run_config.py --n 16384 --k 19 --rns-bits 438 --limbs 8 --limb 0 --proofs 2 --json $O/config5_limb0_k19.json > $O/config5_limb0_k19.txt 2>&1
 # sanitizers on the final code

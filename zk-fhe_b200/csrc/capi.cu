@@ -274,6 +274,15 @@ int zkfhe_init(int device, zkfhe_ctx** out) {
         return ZKFHE_ERR_CUDA;
     }
     ctx->own_stream = true;
+    {   // Poly handles come from the stream-ordered allocator (~20 per proof).  By default the pool hands freed memory back
+        // to the driver at every synchronisation and maps it again on the next allocation; keep it (the polynomials of
+        // the next proof have the same sizes).  Process-wide for this device, idempotent.
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = ctx;
     return ZKFHE_OK;
 }

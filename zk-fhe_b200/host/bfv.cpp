@@ -18,7 +18,10 @@
 // (anyone can forge proofs against it) and exists for tests and benchmarks only.  The reference falls back to such a
 // test setup silently; this tool makes the caller say so.
 // The proof / pk / vk / snark / srs formats are this implementation's own.
+#include <atomic>
 #include <chrono>
+#include <memory>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -126,6 +129,7 @@ int main(int argc, char** argv) {
     uint32_t k = 13, unusable = 109;
     int transcript = host::TRANSCRIPT_POSEIDON;
     bool insecure_srs = false;
+    uint32_t repeat = 0, n_streams = 8;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -137,6 +141,8 @@ int main(int argc, char** argv) {
         else if (a == "--unusable-rows") unusable = (uint32_t)std::stoul(next());
         else if (a == "--srs") srs_path = next();
         else if (a == "--insecure-test-srs") insecure_srs = true;
+        else if (a == "--repeat") repeat = (uint32_t)std::stoul(next());
+        else if (a == "--streams") n_streams = (uint32_t)std::stoul(next());
         else if (a == "--transcript") { std::string t = next(); transcript = t == "blake2b" ? host::TRANSCRIPT_BLAKE2B : host::TRANSCRIPT_POSEIDON; }
         else if (a == "mock" || a == "keygen" || a == "prove" || a == "verify" || a == "setup") cmd = a;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -144,7 +150,8 @@ int main(int argc, char** argv) {
     if (cmd.empty() || (input.empty() && cmd != "setup" && cmd != "verify")) {
         fprintf(stderr, "usage: bfv --name <name> -k <degree> --input <file under data/> {mock|keygen|prove|verify}\n"
                         "       bfv -k <degree> [--srs <file>] setup\n"
-                        "       options: --srs <file> | --insecure-test-srs, --config-path, --data-path, --unusable-rows, --transcript poseidon|blake2b\n");
+                        "       options: --srs <file> | --insecure-test-srs, --config-path, --data-path, --unusable-rows, --transcript poseidon|blake2b\n"
+                        "       prove --repeat <R> [--streams <S>]: prove the input R more times on S proof streams (host threads) and print proofs/s\n");
         return 2;
     }
     if (srs_path.empty()) srs_path = "params/kzg_bn254_" + std::to_string(k) + ".srs";
@@ -289,6 +296,60 @@ int main(int argc, char** argv) {
             dev.check(zkfhe_prove_finish(pr, circ.builder().raw(), &proof, &len));
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             printf("Proving time%s: %.3f ms (%zu proof bytes)\n", pass ? "" : " (cold, incl. one-time allocations)", ms, len);
+        }
+        if (repeat) {
+            // Serving shape: S proofs in flight on one GPU, one host thread + CUDA stream + witness / prover buffers each,
+            // the commitment-key tables and the proving key shared (what bench.py does from Python, here from C++ threads).
+            if (n_streams < 1) n_streams = 1;
+            std::vector<std::unique_ptr<Device>> devs;
+            std::vector<std::unique_ptr<BfvCircuit>> circs;
+            std::vector<zkfhe_prover*> provers(n_streams, nullptr);
+            for (uint32_t i = 0; i < n_streams; i++) {
+                devs.emplace_back(new Device(0));
+                devs[i]->check(zkfhe_share_srs(devs[i]->raw(), dev.raw()));
+                devs[i]->check(zkfhe_set_blocking_sync(devs[i]->raw(), 1));
+                circs.emplace_back(new BfvCircuit(*devs[i]));
+                os_random(seed, 32);
+                devs[i]->check(zkfhe_prove_begin(devs[i]->raw(), pk, seed, transcript, &provers[i]));
+            }
+            std::atomic<uint32_t> next{0};
+            std::atomic<int> failed{0};
+            auto worker = [&](uint32_t i, uint32_t total) {
+                try {
+                    uint8_t g[32], sd[32];
+                    while (next.fetch_add(1) < total) {
+                        circs[i]->builder().reset();
+                        os_random(sd, 32);
+                        devs[i]->check(zkfhe_prove_reset(provers[i], sd));
+                        circs[i]->phase0(in);
+                        devs[i]->check(zkfhe_prove_phase0(provers[i], circs[i]->builder().raw(), g));
+                        circs[i]->phase1(g);
+                        uint8_t* pf = nullptr;
+                        size_t pl = 0;
+                        devs[i]->check(zkfhe_prove_finish(provers[i], circs[i]->builder().raw(), &pf, &pl));
+                        zkfhe_proof_free(pf);
+                    }
+                } catch (const Error& e) {
+                    fprintf(stderr, "stream %u: error (%d): %s\n", i, e.code, e.what());
+                    failed = 1;
+                }
+            };
+            auto run = [&](uint32_t total) {
+                next = 0;
+                std::vector<std::thread> th;
+                for (uint32_t i = 0; i < n_streams; i++) th.emplace_back(worker, i, total);
+                for (auto& t : th) t.join();
+            };
+            run(2 * n_streams);                                    // warm-up: one-time allocations of every stream
+            auto t0 = std::chrono::steady_clock::now();
+            run(repeat);
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("Throughput: %.2f proofs/s (%u proofs from host strings to proof bytes, %u proof streams, %.3f s)\n", repeat / sec, repeat,
+                   n_streams, sec);
+            for (uint32_t i = 0; i < n_streams; i++) zkfhe_prover_free(provers[i]);
+            circs.clear();
+            devs.clear();
+            if (failed) return 1;
         }
         // .snark = "ZKFHESN1" | u32 instances | u32 transcript kind | instances (canonical 32-byte LE) | proof
         uint32_t info[16];
