@@ -834,10 +834,11 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     bool cta_final = groups >= 64 && groups <= 512 && (groups & (groups - 1)) == 0;
     if (const char* e = getenv("ZKFHE_MSM_CTA_FINAL")) cta_final = cta_final && atoi(e) != 0;
     // a column goes through the combine levels when some bucket holds more references than this.  Few-column commits
-    // (16-reference slices, fold lanes walking their own bucket's partial sums) can take 8 slices per bucket before a
-    // combine launch (~90 us on an empty GPU) is cheaper than the extra additions: uniform scalars (~40 +- 20 references
-    // per bucket) then skip it; witness-like columns still exceed it by orders of magnitude.
-    const uint32_t skew_limit = (batch < 32 ? 8 : 3) * SEG;
+    // (16-reference slices, fold lanes walking their own bucket's partial sums) can take 16 slices per bucket before a
+    // combine launch (~95 us on an empty GPU) is cheaper than the extra additions.  Uniform scalars sit at ~40 references
+    // per bucket except for the 64 buckets the short top window feeds (~170 +- 13 each at k = 13), so they stay below it;
+    // witness-like columns exceed it by orders of magnitude.
+    const uint32_t skew_limit = (batch < 32 ? 16 : 3) * SEG;
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;
