@@ -209,6 +209,21 @@ def test_msm_k13_witness_like_columns_match_oracle(ctx):
     assert ps == curve.g1_add(_pt(got[0]), _pt(got[1]))
 
 
+@pytest.mark.parametrize("batch", [1, 2, 3, 31, 33])
+def test_msm_k13_uniform_columns_few_and_many(ctx, batch):
+    """Uniform scalars at config-1 size on both sides of the few-column switch (batch < 32: cluster sort, 16-reference
+    slices, warp fold with the combine level skipped; batch >= 32: one CTA per column, 64-reference slices), all ending
+    in the CTA-wide final reduction: against the C oracle, column by column."""
+    k, n = 13, 1 << 13
+    g, gl = toy_srs(k)
+    ctx.load_srs(k, g=g, g_lagrange=None)
+    rng = np.random.default_rng(4000 + batch)
+    scal = random_fr_mont(rng, batch * n)
+    want = cbind.msm(scal, g, n, batch)
+    got = np.frombuffer(ctx.msm_g1(scal, batch, basis=0), np.uint64).reshape(batch, 8)
+    assert np.array_equal(got, want)
+
+
 def test_msm_small_value_hint_gives_identical_points(ctx):
     """zkfhe_msm_g1_dev_ex(small_values=1) (narrow-window table) == the plain MSM == the oracle, on
     witness-like, full-size, all-zero and single-hot-bucket columns."""
