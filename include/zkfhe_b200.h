@@ -278,8 +278,9 @@ int zkfhe_pk_import(zkfhe_ctx* ctx, const uint8_t* buf, size_t len, zkfhe_pk** o
  *   transcript_kind   1 = Poseidon (what the reference's `prove` runs: snark-verifier's PoseidonTranscript, t = 5,
  *                     rate 4, R_F = 8, R_P = 60; ~1,700 permutations per config-1 proof on the host),
  *                     0 = BLAKE2b (halo2's native transcript; microseconds)
- * The proof is a malloc'd byte string (free with zkfhe_proof_free): commitments as canonical
- * uncompressed points (64 bytes), scalars canonical little-endian (32 bytes), in round order. */
+ * The proof is a malloc'd byte string (free with zkfhe_proof_free), in round order: commitments as halo2 writes a
+ * bn256 G1Affine (32 bytes: x little-endian, bit 6 of the last byte = parity of y, bit 7 = identity), scalars
+ * canonical little-endian (32 bytes). */
 typedef struct zkfhe_prover zkfhe_prover;
 /* `ctx` is the context (stream) the proof runs on; it may differ from the one keygen ran on (same
  * GPU), so several proofs can be in flight on one GPU, one context per host thread, all sharing one

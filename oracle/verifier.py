@@ -75,12 +75,31 @@ def verify(vk, instances, proof, tau, transcript_kind=0, s_g2=None):
 
     def rd_point():
         nonlocal pos
-        x = int.from_bytes(proof[pos:pos + 32], "little")
-        y = int.from_bytes(proof[pos + 32:pos + 64], "little")
-        pos += 64
-        pt = None if x == 0 and y == 0 else (x, y)
-        if pt is not None and (x >= field.P_MOD or y >= field.P_MOD or not curve.is_on_curve(pt)):
-            raise VerifyError("commitment is not a curve point")
+        # 32 bytes as halo2curves writes a bn256 G1Affine: x little-endian, bit 6 of the last byte
+        # = parity of y, bit 7 = identity
+        raw = bytearray(proof[pos:pos + 32])
+        if len(raw) != 32:
+            raise VerifyError("proof truncated")
+        pos += 32
+        inf, odd = bool(raw[31] & 0x80), bool(raw[31] & 0x40)
+        raw[31] &= 0x3F
+        x = int.from_bytes(raw, "little")
+        if inf:
+            if x != 0 or odd:
+                raise VerifyError("commitment is not a curve point")
+            pt = None
+        else:
+            if x >= field.P_MOD:
+                raise VerifyError("commitment is not a curve point")
+            rhs = (x * x * x + 3) % field.P_MOD
+            y = pow(rhs, (field.P_MOD + 1) // 4, field.P_MOD)
+            if y * y % field.P_MOD != rhs:
+                raise VerifyError("commitment is not a curve point")
+            if bool(y & 1) != odd:
+                y = field.P_MOD - y
+            pt = (x, y)
+            if not curve.is_on_curve(pt):
+                raise VerifyError("commitment is not a curve point")
         tr.common_point(pt)
         return pt
 

@@ -50,11 +50,11 @@ def test_cli_mock_keygen_prove(workdir, golden_dir):
     r = _run(workdir, "--input", "bfv/bfv.in", "verify")
     assert r.returncode == 0 and "Snark verified successfully" in r.stdout and "Verification time" in r.stdout, r.stdout + r.stderr
     snark = bytearray(open(workdir / "data" / "bfv.snark", "rb").read())
-    snark[16 + 32 * 5121 + 64 * 10 + 3] ^= 1                    # one bit of an advice commitment
+    snark[16 + 32 * 5121 + 32 * 10 + 3] ^= 1                    # one bit of an advice commitment (32 bytes per point)
     open(workdir / "data" / "bfv.snark", "wb").write(snark)
     r = _run(workdir, "--input", "bfv/bfv.in", "verify")
     assert r.returncode == 1 and "REJECTED" in r.stdout
-    snark[16 + 32 * 5121 + 64 * 10 + 3] ^= 1
+    snark[16 + 32 * 5121 + 32 * 10 + 3] ^= 1
     snark[16 + 32 * 7] ^= 2                                      # a public input (a pk0 coefficient)
     open(workdir / "data" / "bfv.snark", "wb").write(snark)
     r = _run(workdir, "--input", "bfv/bfv.in", "verify")

@@ -212,7 +212,7 @@ def test_msm_k13_witness_like_columns_match_oracle(ctx):
 @pytest.mark.parametrize("batch", [1, 2, 3, 31, 33])
 def test_msm_k13_uniform_columns_few_and_many(ctx, batch):
     """Uniform scalars at config-1 size on both sides of the few-column switch (batch < 32: cluster sort, 16-reference
-    slices, warp fold with the combine level skipped; batch >= 32: one CTA per column, 64-reference slices), all ending
+    slices, warp fold; batch >= 32: one CTA per column, 64-reference slices), all ending
     in the CTA-wide final reduction: against the C oracle, column by column."""
     k, n = 13, 1 << 13
     g, gl = toy_srs(k)

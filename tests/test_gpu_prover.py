@@ -115,7 +115,7 @@ def test_prove_with_the_default_poseidon_transcript(ctx13, pk13, bfv_input):
     assert prover.verify(ctx13, vkb, inst, proof, s_g2)
     assert not prover.verify(ctx13, vkb, inst, proof, s_g2, transcript=0)
     bad = bytearray(proof)
-    bad[64 * 200 + 7] ^= 4
+    bad[32 * 200 + 7] ^= 4                     # inside the x coordinate of an advice commitment (32 bytes per point)
     assert not prover.verify(ctx13, vkb, inst, bytes(bad), s_g2)
     with pytest.raises(verifier.VerifyError):
         verifier.verify(vk, inst, bytes(bad), TAU, transcript_kind=1)
@@ -185,11 +185,16 @@ def test_product_verifier_agrees_with_oracle_verifier(ctx13, pk13, bfv_input):
     proof2, _ = _prove(ctx13, pk13, bfv_input, bytes(range(32)))
     assert proof2 == proof
     rng = random.Random(11)
-    offsets = [5, 64 * 3 + 40, 64 * 197 + 3, len(proof) // 2, len(proof) - 100, len(proof) - 1]
-    offsets += [rng.randrange(len(proof)) for _ in range(6)]
-    for off in offsets:
+    # points travel compressed, as halo2 writes them: 411 x 32 bytes of commitments + 1517 x 32 bytes of evaluations
+    assert len(proof) == 32 * 411 + 32 * 1517
+    offsets = [(5, None), (32 * 3 + 8, None), (32 * 197 + 3, None), (len(proof) // 2, None), (len(proof) - 100, None),
+               (len(proof) - 1, None),
+               (32 * 5 + 31, 6),          # only the y-parity bit of a commitment: the other root, a different point
+               (32 * 7 + 31, 7)]          # the identity flag on a finite point: not an encoding
+    offsets += [(rng.randrange(len(proof)), None) for _ in range(6)]
+    for off, bit in offsets:
         bad = bytearray(proof)
-        bad[off] ^= 1 << rng.randrange(8)
+        bad[off] ^= 1 << (rng.randrange(8) if bit is None else bit)
         assert not _pverify(ctx13, vkb, inst, bytes(bad), s_g2), off
         assert "rejected" in ctx13.last_rejection
         with pytest.raises(verifier.VerifyError):

@@ -832,8 +832,8 @@ inline Fr reference_test_tau() {                       // Montgomery form
 //   BLAKE2B  halo2's own `Blake2bWrite` / `Challenge255` shape: every absorbed item is fed to a running
 //            BLAKE2b-512 with a one-byte tag; a challenge is the digest of the state so far (tag 0 appended),
 //            reduced from 512 bits.  Microseconds per proof; selectable (kind 0).
-// Every written item is also appended to the proof in canonical little-endian form (points
-// uncompressed, x || y, identity = 64 zero bytes), so the verifier replays the same sequence.
+// Every written item is also appended to the proof in canonical little-endian form (scalars 32 bytes; points 32 bytes
+// compressed, see write_point), so the verifier replays the same sequence.
 enum TranscriptKind { TRANSCRIPT_BLAKE2B = 0, TRANSCRIPT_POSEIDON = 1 };
 
 struct Transcript {
@@ -879,12 +879,19 @@ struct Transcript {
         b2.update(x_canon, 32);
         b2.update(y_canon, 32);
     }
+    // The proof carries points the way halo2 writes them (`to_bytes` of halo2curves' bn256 `G1Affine`, SURVEY.md App. C.2
+    // [UPSTREAM-RECALL]): 32 bytes, x little-endian (x < p < 2^254 leaves the two top bits free), bit 6 of the last
+    // byte = parity of y, bit 7 = the identity (whose other bits are zero).  The hash still absorbs both coordinates.
+    static void compress_point(const uint64_t x_canon[4], const uint64_t y_canon[4], uint8_t out[32]) {
+        memcpy(out, x_canon, 32);
+        if ((x_canon[0] | x_canon[1] | x_canon[2] | x_canon[3] | y_canon[0] | y_canon[1] | y_canon[2] | y_canon[3]) == 0) out[31] |= 0x80;
+        else out[31] |= (uint8_t)((y_canon[0] & 1) << 6);
+    }
     void write_point(const uint64_t x_canon[4], const uint64_t y_canon[4]) {
         common_point(x_canon, y_canon);
-        const uint8_t* bx = (const uint8_t*)x_canon;
-        const uint8_t* by = (const uint8_t*)y_canon;
-        proof.insert(proof.end(), bx, bx + 32);
-        proof.insert(proof.end(), by, by + 32);
+        uint8_t c[32];
+        compress_point(x_canon, y_canon, c);
+        proof.insert(proof.end(), c, c + 32);
     }
     Fr squeeze() {
         if (kind == TRANSCRIPT_POSEIDON) {

@@ -833,12 +833,12 @@ int msm_run(zkfhe_ctx* ctx, const fr_t* d_scalars, uint64_t stride, uint32_t log
     // the final reduction as one thread per group (a CTA per column) wherever a column has 64..512 groups
     bool cta_final = groups >= 64 && groups <= 512 && (groups & (groups - 1)) == 0;
     if (const char* e = getenv("ZKFHE_MSM_CTA_FINAL")) cta_final = cta_final && atoi(e) != 0;
-    // a column goes through the combine levels when some bucket holds more references than this.  Few-column commits
-    // (16-reference slices, fold lanes walking their own bucket's partial sums) can take 16 slices per bucket before a
-    // combine launch (~95 us on an empty GPU) is cheaper than the extra additions.  Uniform scalars sit at ~40 references
-    // per bucket except for the 64 buckets the short top window feeds (~170 +- 13 each at k = 13), so they stay below it;
-    // witness-like columns exceed it by orders of magnitude.
-    const uint32_t skew_limit = (batch < 32 ? 16 : 3) * SEG;
+    // a column goes through the combine levels when some bucket holds more references than this: 3 slices for the big
+    // batches, 8 for few-column commits (16-reference slices).  Uniform scalars sit at ~40 references per bucket except for
+    // the 64 buckets the short top window feeds (~170 each at k = 13), so they are still combined; measured: skipping the
+    // combine level for them (limit 16 slices) lengthens the fold lanes of those buckets by more than the ~95 us launch
+    // it saves (sort + reduce 4.39 -> 4.56 ms per proof).
+    const uint32_t skew_limit = (batch < 32 ? 8 : 3) * SEG;
     timed_call_start(ctx);
     for (uint32_t done = 0; done < batch; done += chunk) {
         uint32_t nb = batch - done < chunk ? batch - done : chunk;

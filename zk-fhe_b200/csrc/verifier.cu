@@ -49,6 +49,37 @@ bool on_curve(const Point& p) {
     y = host::fq_to_mont(y);
     return host::fq_mul(y, y) == host::fq_add(host::fq_mul(host::fq_mul(x, x), x), host::fq_from_u64(3));
 }
+// 32-byte compressed point (host::Transcript::compress_point) -> canonical x || y; false when the bytes are not the
+// encoding of a curve point (x >= p, x^3 + 3 not a square, stray bits on the identity).  p = 3 mod 4: sqrt(a) = a^((p+1)/4).
+bool decompress_point(const uint8_t in[32], Point& out) {
+    uint8_t xb[32];
+    memcpy(xb, in, 32);
+    const bool inf = (xb[31] & 0x80) != 0, odd = (xb[31] & 0x40) != 0;
+    xb[31] &= 0x3f;
+    host::Fq x;
+    memcpy(x.l, xb, 32);
+    memset(out.c, 0, sizeof out.c);
+    if (inf) return x.is_zero() && !odd;
+    if (host::fq_geq(x, host::FQ_MOD)) return false;
+    const host::Fq xm = host::fq_to_mont(x);
+    const host::Fq rhs = host::fq_add(host::fq_mul(host::fq_mul(xm, xm), xm), host::fq_from_u64(3));
+    host::Fq e = host::FQ_MOD;                          // (p + 1) / 4: p + 1 does not overflow 256 bits (p < 2^254)
+    e.l[0] += 1;                                        // p is odd and p = 3 mod 4, so the low limb does not carry
+    for (int i = 0; i < 4; i++) e.l[i] = (e.l[i] >> 2) | (i < 3 ? e.l[i + 1] << 62 : 0);
+    host::Fq y = host::FQ_ONE;
+    for (int i = 3; i >= 0; i--)
+        for (int b = 63; b >= 0; b--) {
+            y = host::fq_mul(y, y);
+            if ((e.l[i] >> b) & 1) y = host::fq_mul(y, rhs);
+        }
+    if (!(host::fq_mul(y, y) == rhs)) return false;
+    host::Fq yc = host::fq_from_mont(y);
+    if (yc.is_zero() && odd) return false;              // no point with y = 0 on this curve anyway (-3 is not a cube)
+    if (((yc.l[0] & 1) != 0) != odd) yc = host::fq_sub_raw(host::FQ_MOD, yc);
+    memcpy(out.c, x.l, 32);
+    memcpy(out.c + 4, yc.l, 32);
+    return true;
+}
 g1_affine to_device_point(const Point& p) {
     host::Fq x, y;
     memcpy(x.l, p.c, 32);
@@ -195,11 +226,11 @@ int zkfhe_verify(zkfhe_ctx* ctx, const uint8_t* vk, size_t vk_len, const uint8_t
         host::Transcript tr(transcript_kind);
         size_t pos = 0;
         auto rd_point = [&]() {
-            if (pos + 64 > proof_len) throw Reject{"proof truncated"};
+            if (pos + 32 > proof_len) throw Reject{"proof truncated"};
             Point p;
-            memcpy(p.c, proof + pos, 64);
-            pos += 64;
-            if (!on_curve(p)) throw Reject{"commitment is not a curve point"};
+            const bool ok = decompress_point(proof + pos, p);
+            pos += 32;
+            if (!ok || !on_curve(p)) throw Reject{"commitment is not a curve point"};
             tr.common_point(p.c, p.c + 4);
             return p;
         };
