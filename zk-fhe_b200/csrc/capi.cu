@@ -136,19 +136,98 @@ __global__ void __launch_bounds__(32) k_bench_chain(int kind, uint32_t iters, g1
     if (threadIdx.x == 0) xyzz_store(out, acc);
 }
 
+// kind 6 / 7 -- an EXPERIMENT, not used by the prover: the instruction mix of a 256-bit Montgomery product on the FP64
+// pipe (Emmart, Zheng, Weems, ARITH 2018): limbs of 52 bits held as doubles, each limb product split into two exact
+// doubles by hi = fma_rz(a, b, 2^104), lo = fma_rz(a, b, 2^104 + 2^52 - hi), whose bit patterns are summed as 64-bit
+// integers; five reduction steps, each one low product for m and five limb products m * n_j.  110 DFMA + ~70 DADD on the
+// FP64 pipe and ~125 64-bit integer additions on the ALU pipe per product, no IMAD.  It answers one question (DESIGN.md
+// section 9): is there a second multiply pipe worth feeding beside fmaheavy?  kind 6 runs it on every warp, kind 7 on the
+// odd warps while the even warps run the IMAD product.  (The arithmetic is carried through faithfully enough that the
+// compiler cannot drop it; the result is not checked against a field product.)
+struct d5 { double v[5]; };
+__device__ __forceinline__ double ll_to_d52(long long x) {       // integer < 2^52 -> double, no conversion instruction
+    return __longlong_as_double((x & 0x000fffffffffffffLL) | 0x4330000000000000LL) - 0x1p52;
+}
+__device__ __forceinline__ d5 dfma_mont(const d5& a, const d5& b, const d5& n, double ninv) {
+    const double C1 = 0x1p104, C3 = 0x1p104 + 0x1p52;
+    long long acc[11];
+#pragma unroll
+    for (int k = 0; k < 11; k++) acc[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const double hi = __fma_rz(a.v[i], b.v[j], C1);
+            const double lo = __fma_rz(a.v[i], b.v[j], C3 - hi);
+            acc[i + j + 1] += __double_as_longlong(hi);
+            acc[i + j] += __double_as_longlong(lo);
+        }
+#pragma unroll
+    for (int k = 0; k < 11; k++) acc[k] -= (k < 5 ? k + 1 : 9 - k) * 0x4330000000000000LL + (k ? (k < 6 ? k : 10 - k) * 0x4670000000000000LL : 0);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const double t = ll_to_d52(acc[i]);
+        const double mh = __fma_rz(t, ninv, C1);
+        const double m = __fma_rz(t, ninv, C3 - mh) - 0x1p52;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const double hi = __fma_rz(m, n.v[j], C1);
+            const double lo = __fma_rz(m, n.v[j], C3 - hi);
+            acc[i + j + 1] += __double_as_longlong(hi) - 0x4670000000000000LL;
+            acc[i + j] += __double_as_longlong(lo) - 0x4330000000000000LL;
+        }
+        acc[i + 1] += acc[i] >> 52;
+    }
+    d5 r;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        r.v[k] = ll_to_d52(acc[5 + k]);
+        if (k < 4) acc[6 + k] += acc[5 + k] >> 52;
+    }
+    return r;
+}
+__global__ void __launch_bounds__(256) k_bench_dfma(double* out, uint32_t iters, int mixed, fq_t* out_q) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mixed && ((threadIdx.x >> 5) & 1) == 0) {                 // even warps: the IMAD product of k_bench_mul
+        fq_t a = fe_one<FQ>(), b = fconst<FQ>::r2(), c = fconst<FQ>::r3(), d = fconst<FQ>::r2();
+        a.v[0] += t; c.v[1] ^= t;
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; i++) { a = mul(a, b); c = mul(c, d); }
+        fe_store(out_q + t, add(a, c));
+        return;
+    }
+    d5 a, b, c, d, n;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        a.v[k] = (double)(0x000f123456789abcLL >> k) + t;
+        b.v[k] = (double)(0x0007fedcba987654LL >> k);
+        c.v[k] = (double)(0x000a5a5a5a5a5a5aLL >> k) + 3 * t;
+        d.v[k] = (double)(0x0003c3c3c3c3c3c3LL >> k);
+        n.v[k] = (double)(0x000b85045b681815LL >> (2 * k));
+    }
+    const double ninv = (double)0x000c2e1f593efffffLL;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) { a = dfma_mont(a, b, n, ninv); c = dfma_mont(c, d, n, ninv); }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) s += a.v[k] + c.v[k];
+    out[t] = s;
+}
+
 int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops) {
-    if (kind < 0 || kind > 5 || !iters) return fail(ctx, ZKFHE_ERR_ARG, "microbench: kind in [0,5], iters > 0");
+    if (kind < 0 || kind > 7 || !iters) return fail(ctx, ZKFHE_ERR_ARG, "microbench: kind in [0,7], iters > 0");
     cudaDeviceProp prop;
     ZK_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
     const uint32_t blocks = (uint32_t)prop.multiProcessorCount * 8, threads = 256;
     void* buf;
-    ZK_TRY(ws_get(ctx, "microbench", (size_t)blocks * threads * sizeof(fq_t) + sizeof(g1_xyzz), &buf));
+    ZK_TRY(ws_get(ctx, "microbench", (size_t)blocks * threads * (sizeof(fq_t) + sizeof(double)) + sizeof(g1_xyzz), &buf));
     cudaEvent_t e0, e1;
     ZK_CUDA(ctx, cudaEventCreate(&e0));
     ZK_CUDA(ctx, cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {          // first pass warms up; the second is the one reported
         ZK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
         if (kind == 0) k_bench_mul<<<blocks, threads, 0, ctx->stream>>>((fq_t*)buf, iters);
+        else if (kind >= 6) k_bench_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)((fq_t*)buf + (size_t)blocks * threads), iters, kind == 7, (fq_t*)buf);
         else k_bench_chain<<<1, 32, 0, ctx->stream>>>(kind, iters, (g1_xyzz*)buf);
         ZK_CHECK_LAUNCH(ctx);
         ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
@@ -157,7 +236,7 @@ int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t
     ZK_CUDA(ctx, cudaEventElapsedTime(ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *ops = kind == 0 ? (uint64_t)blocks * threads * iters * 2 : (uint64_t)iters;
+    *ops = kind == 0 || kind >= 6 ? (uint64_t)blocks * threads * iters * 2 : (uint64_t)iters;
     return ZKFHE_OK;
 }
 
