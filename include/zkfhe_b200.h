@@ -77,7 +77,10 @@ int zkfhe_selftest(zkfhe_ctx* ctx, uint32_t n_cases, uint64_t seed, uint32_t* mi
  * `iters` operations on one warp -- 1 XYZZ point addition, 2 mixed addition, 3 field product,
  * 4 field inversion (binary Euclid), 5 field inversion (Fermat).  kinds 6, 7: an experiment the prover does not use --
  * the instruction mix of a Montgomery product on the FP64 pipe (52-bit limbs, fma_rz splitting), on every warp (6)
- * or on the odd warps beside the IMAD product on the even ones (7); `ops` = products of both kinds together. */
+ * or on the odd warps beside the IMAD product on the even ones (7); `ops` = products of both kinds together.  kinds 8, 9:
+ * point additions per second on a full GPU over points gathered from the loaded SRS's window table -- 8 = mixed XYZZ
+ * additions (what the MSM runs), 9 = affine additions in batches of 16 pairs per thread sharing one inversion (an
+ * experiment; the prover does not use it); `ops` = additions. */
 int zkfhe_microbench(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops);
 
 /* ---- stage (3): NTT over BN254 Fr --------------------------------------------------------

@@ -214,19 +214,81 @@ __global__ void __launch_bounds__(256) k_bench_dfma(double* out, uint32_t iters,
     out[t] = s;
 }
 
+// kind 8 / 9 -- the second experiment of DESIGN.md section 9: point additions per second with every SM full, points
+// gathered from the L2-resident window table of the loaded commitment key.
+//   kind 8  what k_msm_accumulate does: one XYZZ accumulator per thread, mixed additions (8M + 2S = 10 products each);
+//   kind 9  batched affine: each thread adds BA_B independent PAIRS of affine points with ONE inversion
+//           (Montgomery's trick: prefix products of the x differences in local memory, binary-Euclid inversion off the
+//           multiply pipe, 6 products per addition) -- the inner operation of a pairwise bucket tree.
+// Neither result is checked here beyond being kept alive; the prover does not use kind 9.
+static constexpr int BA_B = 16;
+__global__ void __launch_bounds__(256) k_bench_madd(const g1_affine* __restrict__ table, uint32_t mask, uint32_t iters, g1_xyzz* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    g1_xyzz acc = xyzz_identity();
+    uint32_t h = t * 2654435761u;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) {
+        h = h * 1664525u + 1013904223u;
+        xyzz_madd(acc, affine_load(table + (h & mask)), (h >> 31) != 0);
+    }
+    xyzz_store(out + t, acc);
+}
+__global__ void __launch_bounds__(256) k_bench_batched_affine(const g1_affine* __restrict__ table, uint32_t mask, uint32_t iters, fq_t* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    fq_t check = fe_zero<FQ>();
+    uint32_t h = t * 2654435761u;
+    fq_t d[BA_B], pre[BA_B];
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it += BA_B) {
+        const uint32_t h0 = h;
+        fq_t run = fe_one<FQ>();
+#pragma unroll 1
+        for (int i = 0; i < BA_B; i++) {                          // forward: prefix products of (x2 - x1)
+            h = h * 1664525u + 1013904223u;
+            const uint32_t ip = h & mask, iq = (ip + 1 + ((h >> 20) & 63)) & mask;      // two distinct table entries
+            d[i] = sub(fe_load_nc(&table[iq].x), fe_load_nc(&table[ip].x));
+            pre[i] = run;
+            run = mul(run, d[i]);
+        }
+        fq_t inv_run = inv(run);                                   // one inversion for the whole batch
+        h = h0;
+        uint32_t idx[BA_B];
+#pragma unroll 1
+        for (int i = 0; i < BA_B; i++) { h = h * 1664525u + 1013904223u; idx[i] = h; }
+#pragma unroll 1
+        for (int i = BA_B - 1; i >= 0; i--) {                      // backward: 1 / d_i, lambda, the sum
+            const uint32_t ip = idx[i] & mask, iq = (ip + 1 + ((idx[i] >> 20) & 63)) & mask;
+            const fq_t dinv = mul(inv_run, pre[i]);
+            inv_run = mul(inv_run, d[i]);
+            const g1_affine P = affine_load(table + ip), Q = affine_load(table + iq);
+            const fq_t lam = mul(sub(Q.y, P.y), dinv);
+            const fq_t x3 = sub(sub(sqr(lam), P.x), Q.x);
+            const fq_t y3 = sub(mul(lam, sub(P.x, x3)), P.y);
+            check = add(check, add(x3, y3));
+        }
+    }
+    fe_store(out + t, check);
+}
+
 int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t* ops) {
-    if (kind < 0 || kind > 7 || !iters) return fail(ctx, ZKFHE_ERR_ARG, "microbench: kind in [0,7], iters > 0");
+    if (kind < 0 || kind > 9 || !iters) return fail(ctx, ZKFHE_ERR_ARG, "microbench: kind in [0,9], iters > 0");
+    if (kind >= 8 && !ctx->basis[0].loaded) return fail(ctx, ZKFHE_ERR_STATE, "microbench kinds 8, 9 read the window table: load an SRS first");
+    if (kind == 9) iters = (iters + BA_B - 1) / BA_B * BA_B;
     cudaDeviceProp prop;
     ZK_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
     const uint32_t blocks = (uint32_t)prop.multiProcessorCount * 8, threads = 256;
     void* buf;
-    ZK_TRY(ws_get(ctx, "microbench", (size_t)blocks * threads * (sizeof(fq_t) + sizeof(double)) + sizeof(g1_xyzz), &buf));
+    ZK_TRY(ws_get(ctx, "microbench", (size_t)blocks * threads * (kind == 8 ? sizeof(g1_xyzz) : sizeof(fq_t) + sizeof(double)) + sizeof(g1_xyzz), &buf));
+    // gather range of kinds 8 / 9: the first 16 window rows of the table (W >= 16 for every window width in use), a power of two
+    const uint32_t tmask = kind >= 8 ? (1u << (ctx->basis[0].log_n + (ctx->basis[0].W >= 16 ? 4 : 0))) - 1 : 0;
     cudaEvent_t e0, e1;
     ZK_CUDA(ctx, cudaEventCreate(&e0));
     ZK_CUDA(ctx, cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {          // first pass warms up; the second is the one reported
         ZK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
         if (kind == 0) k_bench_mul<<<blocks, threads, 0, ctx->stream>>>((fq_t*)buf, iters);
+        else if (kind == 8) k_bench_madd<<<blocks, threads, 0, ctx->stream>>>(ctx->basis[0].table, tmask, iters, (g1_xyzz*)buf);
+        else if (kind == 9) k_bench_batched_affine<<<blocks, threads, 0, ctx->stream>>>(ctx->basis[0].table, tmask, iters, (fq_t*)buf);
         else if (kind >= 6) k_bench_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)((fq_t*)buf + (size_t)blocks * threads), iters, kind == 7, (fq_t*)buf);
         else k_bench_chain<<<1, 32, 0, ctx->stream>>>(kind, iters, (g1_xyzz*)buf);
         ZK_CHECK_LAUNCH(ctx);
@@ -236,7 +298,7 @@ int microbench_run(zkfhe_ctx* ctx, int kind, uint32_t iters, float* ms, uint64_t
     ZK_CUDA(ctx, cudaEventElapsedTime(ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *ops = kind == 0 || kind >= 6 ? (uint64_t)blocks * threads * iters * 2 : (uint64_t)iters;
+    *ops = kind >= 8 ? (uint64_t)blocks * threads * iters : kind == 0 || kind >= 6 ? (uint64_t)blocks * threads * iters * 2 : (uint64_t)iters;
     return ZKFHE_OK;
 }
 
