@@ -340,6 +340,12 @@ int zkfhe_pairing(const uint8_t* g1_point, const uint8_t* g2_point, int referenc
 /* [tau]_2 of the test SRS made by zkfhe_srs_setup (halo2 `ParamsKZG::setup` keeps s_g2 beside the G1
  * powers): tau as a Montgomery Fr element in, 128 bytes (x.c0 | x.c1 | y.c0 | y.c1, Montgomery) out. */
 int zkfhe_srs_g2(const uint8_t* tau_mont32, uint8_t* out128);
+/* The proof's point encoding, host only: canonical affine x || y (64 bytes little-endian, identity = zeros) <-> the 32
+ * bytes halo2 writes for a bn256 G1Affine (x little-endian, bit 6 of the last byte = parity of y, bit 7 = identity;
+ * SURVEY.md App. C.2).  Decompression recovers y = sqrt(x^3 + 3) with that parity and returns ZKFHE_ERR_ARG when the
+ * bytes do not encode a curve point (x >= p, no square root, stray bits beside the identity flag). */
+int zkfhe_point_compress(const uint8_t* xy_canon64, uint8_t* out32);
+int zkfhe_point_decompress(const uint8_t* in32, uint8_t* xy_canon64);
 /* The verifying key as bytes -- the reference's data/<name>.vk written by `keygen`: the layout numbers
  * of the circuit and the commitments of the fixed columns.  Call with buf = NULL to get the size. */
 int zkfhe_vk_export(const zkfhe_pk* pk, uint8_t* buf, size_t cap, size_t* needed);

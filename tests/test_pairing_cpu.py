@@ -92,3 +92,48 @@ def test_pairing_values_fast_path_equals_reference_construction_equals_oracle():
     qb = bytearray(_g2(pairing.G2_GEN))
     assert lib.zkfhe_pairing(_addr(zero_pt), _addr(qb), 0, _addr(one)) == 0          # e(identity, Q) = 1
     assert int.from_bytes(one[:32], "little") * r_inv % P_MOD == 1 and not any(one[32:])
+
+
+def test_proof_point_encoding_round_trips_and_rejects_non_points():
+    """The 32-byte point encoding of the proof (halo2curves' bn256 G1Affine as SURVEY App. C.2 recalls it), host code
+    of the library against the oracle's curve arithmetic: multiples of the generator and their negatives round-trip,
+    the identity is the flag alone, and bytes that are not an encoding are refused."""
+    import ctypes
+    import random
+
+    import zk_fhe_b200
+    from oracle import curve, field
+    lib = zk_fhe_b200.load_library()
+    P = field.P_MOD
+
+    def compress(pt):
+        raw = (b"\0" * 64) if pt is None else pt[0].to_bytes(32, "little") + pt[1].to_bytes(32, "little")
+        src, out = (ctypes.c_char * 64).from_buffer_copy(raw), (ctypes.c_char * 32)()
+        assert lib.zkfhe_point_compress(ctypes.addressof(src), ctypes.addressof(out)) == 0
+        return bytes(out)
+
+    def decompress(enc):
+        src, out = (ctypes.c_char * 32).from_buffer_copy(enc), (ctypes.c_char * 64)()
+        if lib.zkfhe_point_decompress(ctypes.addressof(src), ctypes.addressof(out)) != 0:
+            return "invalid"
+        x, y = int.from_bytes(bytes(out)[:32], "little"), int.from_bytes(bytes(out)[32:], "little")
+        return None if x == 0 and y == 0 else (x, y)
+
+    rnd = random.Random(5)
+    for k in [1, 2, 3, 7, field.R_MOD - 1] + [rnd.randrange(1, field.R_MOD) for _ in range(40)]:
+        pt = curve.g1_mul(curve.G1_GEN, k)
+        for q in (pt, (pt[0], P - pt[1])):
+            enc = compress(q)
+            assert enc == curve.g1_compress(q)                          # the oracle's restatement of the encoding
+            assert len(enc) == 32 and (enc[31] & 0x80) == 0 and ((enc[31] >> 6) & 1) == (q[1] & 1)
+            assert int.from_bytes(enc[:31] + bytes([enc[31] & 0x3F]), "little") == q[0]
+            assert decompress(enc) == q
+    ident = compress(None)
+    assert ident == curve.g1_compress(None)
+    assert ident == b"\0" * 31 + b"\x80" and decompress(ident) is None
+    assert decompress(b"\0" * 31 + b"\xc0") == "invalid"                       # identity flag with a sign bit
+    assert decompress((1).to_bytes(31, "little") + b"\x80") == "invalid"       # identity flag with a non-zero x
+    assert decompress(P.to_bytes(32, "little")) == "invalid"                  # x = p is not canonical
+    non_residue = next(x for x in range(2, 50) if pow((x ** 3 + 3) % P, (P - 1) // 2, P) != 1)
+    assert decompress(non_residue.to_bytes(32, "little")) == "invalid"        # x^3 + 3 is not a square
+    assert decompress(b"\0" * 32) == "invalid"                                # x = 0 without the flag: 3 is not a square mod p

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "zkfhe_pairing": (_c.c_int, [_u8p, _u8p, _c.c_int, _u8p]),
     "zkfhe_srs_g2": (_c.c_int, [_u8p, _u8p]),
     "zkfhe_reference_test_tau": (_c.c_int, [_u8p, _u8p]),
+    "zkfhe_point_compress": (_c.c_int, [_u8p, _u8p]),
+    "zkfhe_point_decompress": (_c.c_int, [_u8p, _u8p]),
     "zkfhe_vk_export": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "zkfhe_verify": (_c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p, _c.c_uint32, _u8p, _c.c_size_t, _u8p, _c.c_int,
                                 _c.POINTER(_c.c_int)]),

@@ -145,6 +145,24 @@ int zkfhe_pairing(const uint8_t* g1_point, const uint8_t* g2_point, int referenc
     return ZKFHE_OK;
 }
 
+// The proof's point encoding on its own (host only): canonical x || y (64 bytes, identity = zeros) <-> the 32 bytes
+// halo2 writes.  Compression does not check the curve equation; decompression returns ZKFHE_ERR_ARG for bytes that
+// are not the encoding of a curve point.
+int zkfhe_point_compress(const uint8_t* xy_canon64, uint8_t* out32) {
+    if (!xy_canon64 || !out32) return ZKFHE_ERR_ARG;
+    uint64_t c[8];
+    memcpy(c, xy_canon64, 64);
+    host::Transcript::compress_point(c, c + 4, out32);
+    return ZKFHE_OK;
+}
+int zkfhe_point_decompress(const uint8_t* in32, uint8_t* xy_canon64) {
+    if (!in32 || !xy_canon64) return ZKFHE_ERR_ARG;
+    Point p;
+    if (!decompress_point(in32, p) || !on_curve(p)) return ZKFHE_ERR_ARG;
+    memcpy(xy_canon64, p.c, 64);
+    return ZKFHE_OK;
+}
+
 // [tau]_2 for the test SRS (`ParamsKZG::setup` keeps s_g2 next to the G1 powers): 128 bytes, Montgomery.
 int zkfhe_srs_g2(const uint8_t* tau_mont32, uint8_t* out128) {
     if (!tau_mont32 || !out128) return ZKFHE_ERR_ARG;
