@@ -694,6 +694,7 @@ inline void poseidon_permute_scalar(Fr s[POSEIDON_T]) {
 }
 // AVX-512 IFMA form (poseidon_ifma.cpp, compiled separately with the vector flags): the products off the S-box chain
 // run on the vector unit; bit-identical results.  `poseidon_permute` is what the transcript calls.
+#ifndef ZKFHE_POSEIDON_IFMA_TU          // (poseidon_ifma.cpp includes this header with internal linkage and defines the two itself)
 void poseidon_permute_ifma(Fr s[POSEIDON_T]);
 bool poseidon_ifma_available();
 inline void poseidon_permute(Fr s[POSEIDON_T]) {
@@ -702,6 +703,9 @@ inline void poseidon_permute(Fr s[POSEIDON_T]) {
 #endif
     poseidon_permute_scalar(s);
 }
+#else
+inline void poseidon_permute(Fr s[POSEIDON_T]) { poseidon_permute_scalar(s); }
+#endif
 inline void poseidon_permute_plain(Fr s[POSEIDON_T]) {
     const int T = POSEIDON_T, half = POSEIDON_RF / 2, rounds = POSEIDON_RF + POSEIDON_RP;
     for (int r = 0; r < rounds; r++) {

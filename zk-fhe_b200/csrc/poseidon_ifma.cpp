@@ -20,12 +20,26 @@
 //
 // Compiled by g++ with -mavx512f -mavx512ifma -mavx512vl (this file only); callers dispatch on cpuid.
 #include <immintrin.h>
+#include <sched.h>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
-#include "host_ff.h"
+#include <vector>
 
-namespace zkfhe { namespace host {
-
+// This translation unit is compiled with AVX-512 enabled.  host_ff.h is all `inline` functions, i.e. COMDAT symbols of
+// which the linker keeps ONE copy for the whole library: a copy compiled here could carry EVEX-encoded instructions into
+// code that runs on CPUs without AVX-512.  So the header is included inside an unnamed namespace (its system headers are
+// included above, at global scope): every helper it defines has internal linkage in this file, and the two exported
+// functions below take the library's `zkfhe::host::Fr` by pointer and reinterpret it as this file's identical copy.
+#define ZKFHE_POSEIDON_IFMA_TU 1
+namespace ifma_tu {
 namespace {
+#include "host_ff.h"
+}
+}
+
+namespace ifma_tu { namespace { namespace zkfhe { namespace host {
 
 // every CPU with AVX-512 IFMA has BMI2 / ADX (poseidon_ifma_available checks both): no per-call dispatch in here
 inline Fr fmul(const Fr& a, const Fr& b) { return mul_adx(a, b); }
@@ -299,10 +313,14 @@ inline void permute(Fr s[POSEIDON_T]) {
     for (int i = 0; i < 5; i++) s[i] = lane_to_fr(X, i);
 }
 
-}  // namespace
+} } } }  // namespace ifma_tu::(unnamed)::zkfhe::host
+
+namespace zkfhe { namespace host {
+
+struct Fr;                     // the library's type (host_ff.h): four little-endian 64-bit limbs, as the copy above
 
 // Same function as host::poseidon_permute_scalar (bit-identical output), inputs and outputs canonical Montgomery.
-void poseidon_permute_ifma(Fr s[POSEIDON_T]) { permute(s); }
+void poseidon_permute_ifma(Fr s[5]) { ifma_tu::zkfhe::host::permute(reinterpret_cast<ifma_tu::zkfhe::host::Fr*>(s)); }
 
 bool poseidon_ifma_available() {
     static const bool ok = [] {
